@@ -1,0 +1,279 @@
+// amer_kernels.cu -- the reference's own early-exercise Monte Carlo scheme (a6 + a7 + a8).
+//   reference include/common.h:168-208 (pathsfinder), src/mc_amer.cpp:23-113 (backward sweep),
+//   include/common.h:98-141 (3x3 inverse + mat-vec).
+//
+// HBM layout (per GPU, n = local path index, Nl local paths = 2 * local antithetic pairs):
+//   paths  double[M][Nl]   row m-1 holds S at date m (row 0 of the reference, S0, is never read by the
+//                          sweep and is not stored). Pair p owns columns p and p + Nl/2, exactly the
+//                          reference's antithetic halves; both stores of a warp are 256 B contiguous.
+//   when   int32[Nl]       exercise date; bit 30 set when the cash flow was booked by the regression
+//                          branch (mc_amer.cpp:100-103), which books payoff(S - E, E) [SURVEY F1]
+//   cash   double[Nl]      TRUE payoff at paths[when][n] -- the value the reference re-gathers at
+//                          mc_amer.cpp:50; carrying it turns that row gather into a coalesced read.
+// exercise_st of the reference is a pure function of (cash, flag): st = flag ? payoff(cp*cash, E)
+// : cash, because cp*cash == S - E exactly for an in-the-money path.
+//
+// Per exercise date: moments kernel (HBM-bound: 8 B S + 12 B state per path) -> [ncclAllReduce of
+// 8 doubles when the job has several GPUs] -> decision kernel (8 B S re-read + 12 B state write for
+// exercising paths); the 3x3 normal equations are solved on the device by every block, in the
+// reference's operation order and without FMA contraction.
+#include "common.cuh"
+#include "reduce.cuh"
+#include "rng.cuh"
+
+namespace pcf {
+
+constexpr int kAmerBlock = 256;
+constexpr int kQuirkBit = 1 << 30;
+constexpr int kMaxDates = 2048;  // discount tables: constant memory -> staged into shared memory per block
+
+__constant__ double c_disc_fwd[kMaxDates + 1];  // exp(-r*dt*k)        as mc_amer.cpp:50 evaluates it
+__constant__ double c_disc_abs[kMaxDates + 1];  // exp(-r*k*dt)        as mc_amer.cpp:110 evaluates it
+
+struct AmerArgs {
+  double S0, E;
+  double adt;   // (r - sigma^2/2) dt
+  double cs;    // sigma*sd (native) | sigma (replay)
+  int cp, M;
+  long long p0;       // first global pair of this GPU
+  long long H;        // local pairs; Nl = 2H
+  unsigned long long seed;
+  const double* w;    // replay: w[(p-p0)*M + (m-1)]
+};
+
+// a6: one thread per antithetic pair, S+ and S- in registers, one Philox block per two dates.
+template <bool kReplay>
+__global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, double* __restrict__ paths,
+                                                                int* __restrict__ when,
+                                                                double* __restrict__ cash) {
+  const PhiloxKey key(a.seed);
+  const long long Nl = 2 * a.H;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.H;
+       p += (long long)gridDim.x * blockDim.x) {
+    double Sp = a.S0, Sm = a.S0;
+    double z0 = 0.0, z1 = 0.0;
+    for (int m = 1; m <= a.M; ++m) {
+      double z;
+      if (kReplay) {
+        z = a.w[p * (long long)a.M + (m - 1)];
+      } else {
+        if ((m - 1) % 2 == 0)
+          normal_pair(key, (uint64_t)(a.p0 + p), (uint32_t)((m - 1) >> 1), PCF_STREAM_AMER, z0, z1);
+        z = ((m - 1) % 2 == 0) ? z0 : z1;
+      }
+      double sw = a.cs * z;
+      Sp *= exp(a.adt + sw);  // common.h:202
+      Sm *= exp(a.adt - sw);  // common.h:203
+      __stcs(paths + (size_t)(m - 1) * Nl + p, Sp);
+      __stcs(paths + (size_t)(m - 1) * Nl + p + a.H, Sm);
+    }
+    // mc_amer.cpp:23-27: exercise_when = M, exercise_st = payoff(S_M)
+    when[p] = a.M;
+    when[p + a.H] = a.M;
+    cash[p] = payoff(Sp, a.E, a.cp);
+    cash[p + a.H] = payoff(Sm, a.E, a.cp);
+  }
+}
+
+// a7 pass 1 (mc_amer.cpp:41-59): moments over in-the-money paths at date m.
+// out[0..7] = n_itm, Sx, Sx^2, Sx^3, Sx^4, Sy, Syx, Syx^2. Products are formed exactly like the
+// reference forms them (left to right, no FMA) so that only the summation order differs.
+__global__ void __launch_bounds__(kAmerBlock) amer_moments_kernel(
+    const double* __restrict__ S_row, const int* __restrict__ when, const double* __restrict__ cash,
+    long long Nl, double E, int cp, int m, int M, double* partials, unsigned int* ticket, double* out) {
+  __shared__ double smem[8 * 2 * 32];
+  extern __shared__ double s_disc[];  // lanes index it with different k: shared memory, not constant
+  for (int k = threadIdx.x; k <= M; k += blockDim.x) s_disc[k] = c_disc_fwd[k];
+  __syncthreads();
+  BlockedComp<8> acc[8];
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < Nl;
+       n += (long long)gridDim.x * blockDim.x) {
+    double S = __ldcs(S_row + n);
+    double pv = payoff(S, E, cp);
+    if (pv > 0.0) {
+      double ex = __dadd_rn(S, -E);
+      int k = (when[n] & ~kQuirkBit) - m;
+      double cont = __dmul_rn(s_disc[k], cash[n]);
+      double ex2 = __dmul_rn(ex, ex), ex3 = __dmul_rn(ex2, ex), ex4 = __dmul_rn(ex3, ex);
+      double yx = __dmul_rn(cont, ex), yx2 = __dmul_rn(yx, ex);
+      acc[0].add(1.0);
+      acc[1].add(ex);
+      acc[2].add(ex2);
+      acc[3].add(ex3);
+      acc[4].add(ex4);
+      acc[5].add(cont);
+      acc[6].add(yx);
+      acc[7].add(yx2);
+    }
+  }
+  Comp v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = acc[i].finish();
+  grid_reduce<8>(v, smem, partials, ticket, out);
+}
+
+// a8: include/common.h:98-141 in the reference's operation order (cyclic %3 indexing, adjugate /
+// determinant, then row-by-row mat-vec accumulated from 0). Returns false when det <= 0.
+__device__ bool solve3_reference_order(const double* mom, double coef[3]) {
+  const double x[3][3] = {{mom[0], mom[1], mom[2]}, {mom[1], mom[2], mom[3]}, {mom[2], mom[3], mom[4]}};
+  const double y[3] = {mom[5], mom[6], mom[7]};
+  double det = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    double t = __dadd_rn(__dmul_rn(x[1][(i + 1) % 3], x[2][(i + 2) % 3]),
+                         -__dmul_rn(x[1][(i + 2) % 3], x[2][(i + 1) % 3]));
+    det = __dadd_rn(det, __dmul_rn(x[0][i], t));
+  }
+  if (!(det > 0.0)) return false;
+  double inv[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double t = __dadd_rn(__dmul_rn(x[(j + 1) % 3][(i + 1) % 3], x[(j + 2) % 3][(i + 2) % 3]),
+                           -__dmul_rn(x[(j + 1) % 3][(i + 2) % 3], x[(j + 2) % 3][(i + 1) % 3]));
+      inv[j][i] = __ddiv_rn(t, det);
+    }
+  for (int i = 0; i < 3; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < 3; ++j) s = __dadd_rn(s, __dmul_rn(inv[i][j], y[j]));
+    coef[i] = s;
+  }
+  return true;
+}
+
+// a7 pass 2 (mc_amer.cpp:73-106): exercise decision at date m from the (all-reduced) moments.
+__global__ void __launch_bounds__(kAmerBlock) amer_decide_kernel(
+    const double* __restrict__ S_row, int* __restrict__ when, double* __restrict__ cash, long long Nl,
+    double E, int cp, int m, const double* __restrict__ mom, int* err_flag) {
+  __shared__ double s_coef[3];
+  __shared__ int s_mode;  // 0 skip, 1 few-paths branch, 2 regression branch
+  if (threadIdx.x == 0) {
+    double cnt = mom[0];
+    if (cnt == 0.0) {
+      s_mode = 0;
+    } else if (cnt <= 2.0) {
+      s_mode = 1;
+    } else {
+      double coef[3];
+      if (solve3_reference_order(mom, coef)) {
+        s_mode = 2;
+        s_coef[0] = coef[0]; s_coef[1] = coef[1]; s_coef[2] = coef[2];
+      } else {
+        s_mode = 0;
+        if (blockIdx.x == 0) atomicExch(err_flag, PCF_ESINGULAR);
+      }
+    }
+  }
+  __syncthreads();
+  const int mode = s_mode;
+  if (mode == 0) return;
+  const double c0 = s_coef[0], c1 = s_coef[1], c2 = s_coef[2];
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < Nl;
+       n += (long long)gridDim.x * blockDim.x) {
+    double S = __ldcs(S_row + n);
+    double pv = payoff(S, E, cp);
+    if (!(pv > 0.0)) continue;
+    if (mode == 2) {
+      double x = __dadd_rn(S, -E);
+      if (x == -1.0) continue;  // the reference's sentinel collision (mc_amer.cpp:32,98)
+      double yhat = __dadd_rn(__dadd_rn(c0, __dmul_rn(c1, x)), __dmul_rn(c2, __dmul_rn(x, x)));
+      double pq = payoff(x, E, cp);  // payoff of the SHIFTED value (mc_amer.cpp:100)
+      if (pq > yhat) {
+        when[n] = m | kQuirkBit;
+        cash[n] = pv;
+      }
+    } else {
+      // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against discounted cash flow
+      int k = (when[n] & ~kQuirkBit) - m;
+      double cont = __dmul_rn(c_disc_fwd[k], cash[n]);
+      if (pv > cont) {
+        when[n] = m;
+        cash[n] = pv;
+      }
+    }
+  }
+}
+
+// mc_amer.cpp:109-111: sum of discounted booked cash flows (+ sum of squares for the error bar).
+__global__ void __launch_bounds__(kAmerBlock) amer_final_kernel(const int* __restrict__ when,
+                                                                const double* __restrict__ cash,
+                                                                long long Nl, double E, int cp, int M,
+                                                                double* partials, unsigned int* ticket,
+                                                                double* out) {
+  __shared__ double smem[2 * 2 * 32];
+  extern __shared__ double s_disc[];
+  for (int k = threadIdx.x; k <= M; k += blockDim.x) s_disc[k] = c_disc_abs[k];
+  __syncthreads();
+  BlockedComp<8> s1, s2;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < Nl;
+       n += (long long)gridDim.x * blockDim.x) {
+    int wq = when[n];
+    double cs = cash[n];
+    double st = (wq & kQuirkBit) ? payoff((double)cp * cs, E, cp) : cs;
+    double v = (st != 0.0) ? __dmul_rn(s_disc[wq & ~kQuirkBit], st) : 0.0;
+    s1.add(v);
+    s2.add(v * v);
+  }
+  Comp v[2] = {s1.finish(), s2.finish()};
+  grid_reduce<2>(v, smem, partials, ticket, out);
+}
+
+// Host driver for one GPU. Enqueues everything on c.stream; result (sum, sumsq of discounted cash
+// flows over local paths) lands in c.d_out[0..1]; c.d_out[8..15] is the per-date moment vector.
+int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset) {
+  const int M = p.M;
+  if (M > kMaxDates) {
+    set_last_error("mc_amer: M exceeds kMaxDates");
+    return PCF_EINVAL;
+  }
+  const long long H = pairs.size(), Nl = 2 * H;
+  const double dt = p.T / M;
+  // discount tables, evaluated on the host with the reference's own expressions (glibc exp)
+  static thread_local double fwd[kMaxDates + 1], ab[kMaxDates + 1];
+  for (int k = 0; k <= M; ++k) {
+    fwd[k] = exp(-p.r * dt * (double)k);  // exp(-r*dt*(exercise_when[n]-m))   mc_amer.cpp:50
+    ab[k] = exp(-p.r * (double)k * dt);   // exp(-r*exercise_when[n]*dt)       mc_amer.cpp:110
+  }
+  PCF_CUDA(cudaMemcpyToSymbolAsync(c_disc_fwd, fwd, sizeof(double) * (M + 1), 0, cudaMemcpyHostToDevice, c.stream));
+  PCF_CUDA(cudaMemcpyToSymbolAsync(c_disc_abs, ab, sizeof(double) * (M + 1), 0, cudaMemcpyHostToDevice, c.stream));
+
+  char* base = (char*)c.workspace + ws_offset;
+  double* paths = (double*)base;
+  double* cash = paths + (size_t)M * Nl;
+  int* when = (int*)(cash + Nl);
+
+  AmerArgs a;
+  a.S0 = p.S0; a.E = p.E; a.cp = p.cp; a.M = M;
+  a.adt = (p.r - 0.5 * p.sigma * p.sigma) * dt;
+  a.cs = d_replay ? p.sigma : p.sigma * sqrt(dt);
+  a.p0 = pairs.begin; a.H = H; a.seed = p.seed; a.w = d_replay;
+
+  int grid_gen = grid_for(c, H, kAmerBlock, 8);
+  if (d_replay)
+    amer_paths_kernel<true><<<grid_gen, kAmerBlock, 0, c.stream>>>(a, paths, when, cash);
+  else
+    amer_paths_kernel<false><<<grid_gen, kAmerBlock, 0, c.stream>>>(a, paths, when, cash);
+  c.launches++;
+  PCF_CUDA(cudaGetLastError());
+
+  int grid = grid_for(c, Nl, kAmerBlock, 8);
+  double* mom = c.d_out + 8;
+  for (int m = M - 1; m > 0; --m) {
+    const double* row = paths + (size_t)(m - 1) * Nl;
+    amer_moments_kernel<<<grid, kAmerBlock, sizeof(double) * (M + 1), c.stream>>>(
+        row, when, cash, Nl, p.E, p.cp, m, M, c.d_partials, c.d_ticket, mom);
+    PCF_TRY(allreduce_sum(c, mom, 8));
+    amer_decide_kernel<<<grid, kAmerBlock, 0, c.stream>>>(row, when, cash, Nl, p.E, p.cp, m, mom, c.d_flag);
+    c.launches += 2;
+  }
+  amer_final_kernel<<<grid, kAmerBlock, sizeof(double) * (M + 1), c.stream>>>(when, cash, Nl, p.E, p.cp, M,
+                                                                               c.d_partials, c.d_ticket, c.d_out);
+  c.launches++;
+  PCF_CUDA(cudaGetLastError());
+  return PCF_OK;
+}
+
+size_t amer_workspace_bytes(long long local_pairs, int M) {
+  size_t Nl = 2 * (size_t)local_pairs;
+  return (size_t)M * Nl * 8 + Nl * 8 + Nl * 4 + 256;
+}
+
+}  // namespace pcf

@@ -1,0 +1,82 @@
+// common.cuh -- per-GPU context, error plumbing and shard arithmetic shared by the method files.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include "../../include/pcf.h"
+
+namespace pcf {
+
+void set_last_error(const std::string& s);
+
+#define PCF_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::pcf::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+      return (_e == cudaErrorMemoryAllocation) ? PCF_ENOMEM : PCF_ECUDA;                      \
+    }                                                                                         \
+  } while (0)
+
+#define PCF_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != PCF_OK) return _s; \
+  } while (0)
+
+constexpr int kMaxBlocks = 148 * 16;  // upper bound on any reduction grid
+constexpr int kMaxMoments = 8;
+
+// One context = one GPU of the job (one per process under torchrun, `gpus` of them in the
+// single-process front ends).
+struct Ctx {
+  int device = 0;
+  int rank = 0, world = 1;   // position in the job
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  void* comm = nullptr;      // ncclComm_t, null when world == 1
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double* d_partials = nullptr;    // kMaxBlocks * kMaxMoments * 2 doubles
+  unsigned int* d_ticket = nullptr;
+  double* d_out = nullptr;         // small result vector (64 doubles)
+  int* d_flag = nullptr;           // device-side error flag
+  double* h_out = nullptr;         // pinned mirror of d_out
+  void* workspace = nullptr;       // grow-only scratch (mc_amer path store, replay streams)
+  size_t workspace_bytes = 0;
+  int launches = 0;                // kernels launched in the current call
+};
+
+int ctx_reserve(Ctx& c, size_t bytes);  // ensures c.workspace >= bytes
+int allreduce_sum(Ctx& c, double* d_buf, int count);  // in place, on c.stream; no-op if world == 1
+
+// Contiguous block partition of `units` over the job: rank g takes
+// [g*ceil(U/G), min(U,(g+1)*ceil(U/G))).
+struct Shard {
+  long long begin, end;
+  __host__ __device__ long long size() const { return end > begin ? end - begin : 0; }
+};
+inline Shard shard_of(long long units, int rank, int world) {
+  long long per = (units + world - 1) / world;
+  long long b = per * rank, e = b + per;
+  if (b > units) b = units;
+  if (e > units) e = units;
+  return Shard{b, e};
+}
+
+// Reduction-grid sizing: persistent-style grids in multiples of the SM count.
+inline int grid_for(const Ctx& c, long long work_items, int block, int blocks_per_sm) {
+  long long need = (work_items + block - 1) / block;
+  long long cap = (long long)c.sm_count * blocks_per_sm;
+  if (cap > kMaxBlocks) cap = kMaxBlocks;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// reference include/common.h:56-60
+__host__ __device__ __forceinline__ double payoff(double St, double E, int cp) {
+  double v = (double)cp * (St - E);
+  return v > 0.0 ? v : 0.0;
+}
+
+}  // namespace pcf

@@ -1,0 +1,280 @@
+// mc_kernels.cu -- European (a1), Asian (a3) and basket (a4+a5) Monte Carlo kernels, sm_100a FP64.
+// One path per thread iteration, state in registers, Philox normals generated in-register,
+// compensated (sum, sum^2) reduced thread -> warp -> block -> grid. No tensor cores: nothing here
+// is a dense contraction; the bound is the FP64 pipe.
+#include "common.cuh"
+#include "reduce.cuh"
+#include "rng.cuh"
+
+namespace pcf {
+
+constexpr int kBlock = 256;
+
+// ------------------------------------------------------------------------------------------------
+// a1  reference src/mc_eur.cpp:23-26
+struct EurArgs {
+  double S0, E, drift, sigma, sqrtT;  // drift = (r - sigma^2/2) T
+  int cp;
+  long long N;        // global path count
+  long long k0, k1;   // this GPU's pair range: paths 2k, 2k+1
+  unsigned long long seed;
+  const double* w;    // replay: w[n - 2*k0], already N(0,T)
+};
+
+template <bool kReplay>
+__global__ void __launch_bounds__(kBlock) mc_eur_kernel(EurArgs a, double* partials,
+                                                        unsigned int* ticket, double* out) {
+  __shared__ double smem[2 * 2 * 32];
+  const PhiloxKey key(a.seed);
+  BlockedComp<4> s1, s2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = a.k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < a.k1; k += stride) {
+    double w0, w1;
+    const bool has2 = (2 * k + 1 < a.N);
+    if (kReplay) {
+      w0 = a.w[2 * (k - a.k0)];
+      w1 = has2 ? a.w[2 * (k - a.k0) + 1] : 0.0;
+    } else {
+      double z0, z1;
+      normal_pair(key, (uint64_t)k, 0u, PCF_STREAM_EUR, z0, z1);
+      w0 = a.sqrtT * z0;
+      w1 = a.sqrtT * z1;
+    }
+    double v0 = payoff(a.S0 * exp(fma(a.sigma, w0, a.drift)), a.E, a.cp);
+    double v1 = has2 ? payoff(a.S0 * exp(fma(a.sigma, w1, a.drift)), a.E, a.cp) : 0.0;
+    s1.add(v0 + v1);
+    s2.add(fma(v0, v0, v1 * v1));
+  }
+  Comp v[2] = {s1.finish(), s2.finish()};
+  grid_reduce<2>(v, smem, partials, ticket, out);
+}
+
+int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay) {
+  EurArgs a;
+  a.S0 = p.S0; a.E = p.E; a.sigma = p.sigma; a.cp = p.cp; a.N = p.N;
+  a.drift = (p.r - p.sigma * p.sigma / 2) * p.T;
+  a.sqrtT = sqrt(p.T);
+  a.k0 = pairs.begin; a.k1 = pairs.end;
+  a.seed = p.seed; a.w = d_replay;
+  int grid = grid_for(c, pairs.size(), kBlock, 8);
+  if (d_replay)
+    mc_eur_kernel<true><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+  else
+    mc_eur_kernel<false><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+  c.launches++;
+  PCF_CUDA(cudaGetLastError());
+  return PCF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a3  reference src/mc_asia.cpp:27-37
+struct AsiaArgs {
+  double S0, E;
+  double c0;     // 1 + r dt / 2
+  double ch;     // (sigma/2) * sd      (native)  |  sigma/2 (replay)
+  double cs;     // sigma * sd          (native)  |  sigma   (replay)
+  double adt;    // (r - sigma^2/2) dt
+  double invM;   // payoff on I / M  (division kept: see kernel)
+  int cp, M;
+  long long n0, n1;
+  unsigned long long seed;
+  const double* dB;  // replay: dB[(n-n0)*M + m]
+};
+
+__device__ __forceinline__ void asia_step(double& S, double& I, double z, const AsiaArgs& a) {
+  I = fma(S, fma(a.ch, z, a.c0), I);   // I += St*(1 + r dt/2 + sigma dB/2), pre-update St  (:33)
+  S *= exp(fma(a.cs, z, a.adt));       // St *= exp((r - sigma^2/2) dt + sigma dB)            (:34)
+}
+
+template <bool kReplay>
+__global__ void __launch_bounds__(kBlock) mc_asia_kernel(AsiaArgs a, double* partials,
+                                                         unsigned int* ticket, double* out) {
+  __shared__ double smem[2 * 2 * 32];
+  const PhiloxKey key(a.seed);
+  Comp s1, s2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const double Md = (double)a.M;
+  for (long long n = a.n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < a.n1; n += stride) {
+    double S = a.S0, I = 0.0;
+    if (kReplay) {
+      const double* z = a.dB + (n - a.n0) * (long long)a.M;
+      for (int m = 0; m < a.M; ++m) asia_step(S, I, z[m], a);
+    } else {
+      int m = 0;
+      for (; m + 1 < a.M; m += 2) {
+        double z0, z1;
+        normal_pair(key, (uint64_t)n, (uint32_t)(m >> 1), PCF_STREAM_ASIA, z0, z1);
+        asia_step(S, I, z0, a);
+        asia_step(S, I, z1, a);
+      }
+      if (m < a.M) {
+        double z0, z1;
+        normal_pair(key, (uint64_t)n, (uint32_t)(m >> 1), PCF_STREAM_ASIA, z0, z1);
+        asia_step(S, I, z0, a);
+      }
+    }
+    double v = payoff(I / Md, a.E, a.cp);  // :36
+    s1.add(v);
+    s2.add(v * v);
+  }
+  Comp v[2] = {s1, s2};
+  grid_reduce<2>(v, smem, partials, ticket, out);
+}
+
+int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay) {
+  AsiaArgs a;
+  const double dt = (double)p.T / (double)p.M;
+  const double sd = sqrt(dt);
+  a.S0 = p.S0; a.E = p.E; a.cp = p.cp; a.M = p.M;
+  a.c0 = 1 + p.r * dt / 2;
+  a.adt = (p.r - p.sigma * p.sigma / 2) * dt;
+  a.ch = d_replay ? p.sigma / 2 : (p.sigma / 2) * sd;
+  a.cs = d_replay ? p.sigma : p.sigma * sd;
+  a.invM = 1.0 / (double)p.M;
+  a.n0 = paths.begin; a.n1 = paths.end;
+  a.seed = p.seed; a.dB = d_replay;
+  int grid = grid_for(c, paths.size(), kBlock, 8);
+  if (d_replay)
+    mc_asia_kernel<true><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+  else
+    mc_asia_kernel<false><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+  c.launches++;
+  PCF_CUDA(cudaGetLastError());
+  return PCF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a4 + a5  reference include/mvn.h:78-80 (samples = L * Z) and src/mc_eur_multi.cpp:26-33.
+// L (row-major, lower) sits in constant memory: every lane reads the same L[a][k] at the same
+// time, which is the constant cache's broadcast case.
+__constant__ double c_L[PCF_MAX_ASSETS * PCF_MAX_ASSETS];
+
+struct BasketArgs {
+  double E, drift, sigma;  // drift = (r - sigma^2/2) T   (no sqrt(T) anywhere: SURVEY F9)
+  double wS0;              // (1/d) * S0
+  int cp, d;
+  long long n0, n1;
+  unsigned long long seed;
+  const double* Z;  // replay: Z[(n-n0)*d + a]
+};
+
+template <int D, bool kReplay>
+__global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, double* partials,
+                                                           unsigned int* ticket, double* out) {
+  __shared__ double smem[2 * 2 * 32];
+  const PhiloxKey key(a.seed);
+  Comp s1, s2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long n = a.n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < a.n1; n += stride) {
+    double bt[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) bt[i] = 0.0;
+    // column sweep of the triangular product: z_k is consumed as soon as it is drawn
+#pragma unroll
+    for (int j = 0; j < D / 2 + (D & 1); ++j) {
+      if (2 * j < a.d) {
+        double z0, z1;
+        if (kReplay) {
+          const double* z = a.Z + (n - a.n0) * (long long)a.d;
+          z0 = z[2 * j];
+          z1 = (2 * j + 1 < a.d) ? z[2 * j + 1] : 0.0;
+        } else {
+          normal_pair(key, (uint64_t)n, (uint32_t)j, PCF_STREAM_BASKET, z0, z1);
+        }
+#pragma unroll
+        for (int i = 2 * j; i < D; ++i) bt[i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j], z0, bt[i]);
+        if (2 * j + 1 < D) {
+#pragma unroll
+          for (int i = 2 * j + 1; i < D; ++i)
+            bt[i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j + 1], z1, bt[i]);
+        }
+      }
+    }
+    double basket = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+      if (i < a.d) basket = fma(a.wS0, exp(fma(a.sigma, bt[i], a.drift)), basket);  // :30
+    double v = payoff(basket, a.E, a.cp);
+    s1.add(v);
+    s2.add(v * v);
+  }
+  Comp v[2] = {s1, s2};
+  grid_reduce<2>(v, smem, partials, ticket, out);
+}
+
+template <int D>
+static void launch_basket(Ctx& c, const BasketArgs& a, int grid, bool replay) {
+  if (replay)
+    mc_basket_kernel<D, true><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+  else
+    mc_basket_kernel<D, false><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+}
+
+int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-major */,
+                  Shard paths, const double* d_replay) {
+  const int d = p.assets;
+  double Lpad[PCF_MAX_ASSETS * PCF_MAX_ASSETS] = {0};
+  for (int i = 0; i < d; ++i)
+    for (int k = 0; k <= i; ++k) Lpad[i * PCF_MAX_ASSETS + k] = L_host[i * d + k];
+  PCF_CUDA(cudaMemcpyToSymbolAsync(c_L, Lpad, sizeof(Lpad), 0, cudaMemcpyHostToDevice, c.stream));
+  BasketArgs a;
+  a.E = p.E; a.sigma = p.sigma; a.cp = p.cp; a.d = d;
+  a.drift = (p.r - p.sigma * p.sigma / 2) * p.T;
+  a.wS0 = (1.0 / (double)d) * p.S0;
+  a.n0 = paths.begin; a.n1 = paths.end;
+  a.seed = p.seed; a.Z = d_replay;
+  int grid = grid_for(c, paths.size(), kBlock, 4);
+  const bool rp = d_replay != nullptr;
+  if (d <= 2) launch_basket<2>(c, a, grid, rp);
+  else if (d <= 4) launch_basket<4>(c, a, grid, rp);
+  else if (d <= 8) launch_basket<8>(c, a, grid, rp);
+  else if (d <= 16) launch_basket<16>(c, a, grid, rp);
+  else launch_basket<32>(c, a, grid, rp);
+  c.launches++;
+  PCF_CUDA(cudaGetLastError());
+  return PCF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagnostics: the raw generator and the normal stream, for KATs and replay dumps.
+__global__ void philox_kat_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed,
+                                  uint32_t* out) {
+  const PhiloxKey key(seed);
+  uint32_t x[4];
+  philox4x32_10(key, c0, c1, c2, c3, x);
+  for (int i = 0; i < 4; ++i) out[i] = x[i];
+}
+
+__global__ void normal_stream_kernel(uint64_t seed, uint32_t stream, uint64_t index0, long long count,
+                                     int T, double scale, double* out) {
+  const PhiloxKey key(seed);
+  const int blocks = (T + 1) / 2;
+  const long long total = count * blocks;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    long long i = g / blocks;
+    int j = (int)(g - i * blocks);
+    double z0, z1;
+    normal_pair(key, index0 + (uint64_t)i, (uint32_t)j, stream, z0, z1);
+    out[i * (long long)T + 2 * j] = scale * z0;
+    if (2 * j + 1 < T) out[i * (long long)T + 2 * j + 1] = scale * z1;
+  }
+}
+
+int run_philox_kat(Ctx& c, const unsigned int ctr[4], const unsigned int key[2], uint32_t* d_out) {
+  uint64_t seed = ((uint64_t)key[1] << 32) | key[0];
+  philox_kat_kernel<<<1, 1, 0, c.stream>>>(ctr[0], ctr[1], ctr[2], ctr[3], seed, d_out);
+  PCF_CUDA(cudaGetLastError());
+  return PCF_OK;
+}
+
+int run_normal_stream(Ctx& c, uint64_t seed, uint32_t stream, uint64_t index0, long long count, int T,
+                      double scale, double* d_out) {
+  long long total = count * ((T + 1) / 2);
+  int grid = grid_for(c, total, kBlock, 8);
+  normal_stream_kernel<<<grid, kBlock, 0, c.stream>>>(seed, stream, index0, count, T, scale, d_out);
+  PCF_CUDA(cudaGetLastError());
+  return PCF_OK;
+}
+
+}  // namespace pcf

@@ -1,0 +1,583 @@
+// pcf_api.cu -- the C ABI of include/pcf.h: context set, NCCL plumbing, per-method drivers.
+//
+// Job shapes:
+//   * pcf_init(G): one process, G GPUs, one host thread per GPU for the duration of a call
+//     (the front ends' trailing [gpus] argument);
+//   * pcf_init_rank(rank, world, device, id): one process per GPU (torchrun), NCCL communicator
+//     bootstrapped from a caller-distributed unique id.
+// In both, units (paths / antithetic pairs / term pairs) are split into contiguous global index
+// ranges and the partial moments meet in one ncclAllReduce on the compute stream
+// (replaces MPI_Reduce, reference src/mc_eur_mpi.cpp:36 etc.).
+// NCCL is bound lazily through dlopen("libnccl.so.2") so that single-GPU use has no NCCL
+// dependency and a host process that already carries NCCL (PyTorch) shares its copy.
+#include <dlfcn.h>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include "common.cuh"
+
+namespace pcf {
+
+// ---- method drivers implemented in the kernel files --------------------------------------------
+int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay);
+int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay);
+int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host, Shard paths, const double* d_replay);
+int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset);
+size_t amer_workspace_bytes(long long local_pairs, int M);
+int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid);
+void binom_lattice(double r, double sigma, double T, long long N, double& u, double& d, double& p, double& q);
+int run_philox_kat(Ctx& c, const unsigned int ctr[4], const unsigned int key[2], uint32_t* d_out);
+int run_normal_stream(Ctx& c, uint64_t seed, uint32_t stream, uint64_t index0, long long count, int T,
+                      double scale, double* d_out);
+int run_fp64_peak(Ctx& c, double seconds_target, double* dfma_per_sec);
+int run_hbm_peak(Ctx& c, long long bytes, double* bytes_per_sec);
+
+// ---- error text --------------------------------------------------------------------------------
+static std::mutex g_err_mu;
+static std::string g_last_error;
+void set_last_error(const std::string& s) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_last_error = s;
+}
+
+// ---- NCCL, bound at run time -------------------------------------------------------------------
+typedef struct { char internal[128]; } NcclId;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.lib) return PCF_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names)
+    if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!h) {
+    set_last_error(std::string("dlopen(libnccl.so.2): ") + dlerror());
+    return PCF_ENCCL;
+  }
+#define PCF_SYM(field, name)                                   \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                   \
+  if (!g_nccl.field) {                                         \
+    set_last_error(std::string("dlsym ") + name + " failed");  \
+    return PCF_ENCCL;                                          \
+  }
+  PCF_SYM(GetUniqueId, "ncclGetUniqueId");
+  PCF_SYM(CommInitRank, "ncclCommInitRank");
+  PCF_SYM(CommInitAll, "ncclCommInitAll");
+  PCF_SYM(CommDestroy, "ncclCommDestroy");
+  PCF_SYM(AllReduce, "ncclAllReduce");
+  PCF_SYM(GetErrorString, "ncclGetErrorString");
+#undef PCF_SYM
+  g_nccl.lib = h;
+  return PCF_OK;
+}
+
+#define PCF_NCCL(expr)                                                                   \
+  do {                                                                                   \
+    int _r = (expr);                                                                     \
+    if (_r != 0) {                                                                       \
+      set_last_error(std::string(#expr) + ": " + g_nccl.GetErrorString(_r));             \
+      return PCF_ENCCL;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+int allreduce_sum(Ctx& c, double* d_buf, int count) {
+  if (c.world <= 1 || !c.comm) return PCF_OK;
+  PCF_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, c.comm, c.stream));
+  return PCF_OK;
+}
+
+// ---- context set -------------------------------------------------------------------------------
+static std::vector<Ctx> g_ctx;
+
+static int ctx_open(Ctx& c, int device, int rank, int world) {
+  c.device = device; c.rank = rank; c.world = world;
+  PCF_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PCF_CUDA(cudaGetDeviceProperties(&prop, device));
+  c.sm_count = prop.multiProcessorCount;
+  PCF_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  PCF_CUDA(cudaEventCreate(&c.ev0));
+  PCF_CUDA(cudaEventCreate(&c.ev1));
+  PCF_CUDA(cudaMalloc(&c.d_partials, sizeof(double) * kMaxBlocks * kMaxMoments * 2));
+  PCF_CUDA(cudaMalloc(&c.d_ticket, sizeof(unsigned int)));
+  PCF_CUDA(cudaMalloc(&c.d_out, sizeof(double) * 64));
+  PCF_CUDA(cudaMalloc(&c.d_flag, sizeof(int)));
+  PCF_CUDA(cudaMemset(c.d_ticket, 0, sizeof(unsigned int)));
+  PCF_CUDA(cudaMemset(c.d_out, 0, sizeof(double) * 64));
+  PCF_CUDA(cudaMemset(c.d_flag, 0, sizeof(int)));
+  PCF_CUDA(cudaMallocHost(&c.h_out, sizeof(double) * 64));
+  return PCF_OK;
+}
+
+static void ctx_close(Ctx& c) {
+  cudaSetDevice(c.device);
+  if (c.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.comm);
+  if (c.workspace) cudaFree(c.workspace);
+  if (c.h_out) cudaFreeHost(c.h_out);
+  if (c.d_flag) cudaFree(c.d_flag);
+  if (c.d_out) cudaFree(c.d_out);
+  if (c.d_ticket) cudaFree(c.d_ticket);
+  if (c.d_partials) cudaFree(c.d_partials);
+  if (c.ev0) cudaEventDestroy(c.ev0);
+  if (c.ev1) cudaEventDestroy(c.ev1);
+  if (c.stream) cudaStreamDestroy(c.stream);
+  c = Ctx();
+}
+
+int ctx_reserve(Ctx& c, size_t bytes) {
+  if (bytes <= c.workspace_bytes) return PCF_OK;
+  if (c.workspace) {
+    PCF_CUDA(cudaFree(c.workspace));
+    c.workspace = nullptr;
+    c.workspace_bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&c.workspace, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error("cudaMalloc(workspace, " + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
+    return PCF_ENOMEM;
+  }
+  c.workspace_bytes = bytes;
+  return PCF_OK;
+}
+
+// Runs fn(ctx) for every local context: inline when there is one, one host thread per GPU otherwise.
+template <class F>
+static int for_each_ctx(F fn) {
+  if (g_ctx.empty()) return PCF_ENOINIT;
+  if (g_ctx.size() == 1) {
+    cudaSetDevice(g_ctx[0].device);
+    return fn(g_ctx[0]);
+  }
+  std::vector<int> st(g_ctx.size(), PCF_OK);
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < g_ctx.size(); ++i)
+    th.emplace_back([&, i] {
+      cudaSetDevice(g_ctx[i].device);
+      st[i] = fn(g_ctx[i]);
+    });
+  for (auto& t : th) t.join();
+  for (int s : st)
+    if (s != PCF_OK) return s;
+  return PCF_OK;
+}
+
+// Uploads this GPU's slice [off, off+len) of a host replay stream into the context workspace.
+static int upload_replay(Ctx& c, const double* host, long long off, long long len, size_t ws_offset,
+                         const double** d_ptr) {
+  PCF_TRY(ctx_reserve(c, ws_offset + (size_t)(len > 0 ? len : 1) * sizeof(double)));
+  double* d = (double*)((char*)c.workspace + ws_offset);
+  if (len > 0)
+    PCF_CUDA(cudaMemcpyAsync(d, host + off, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  *d_ptr = d;
+  return PCF_OK;
+}
+
+// Common tail of every method: [allreduce of k doubles] -> event -> D2H -> sync.
+static int finish_call(Ctx& c, int k, double* host_vals, double* seconds_kernel, int* flag) {
+  PCF_TRY(allreduce_sum(c, c.d_out, k));
+  PCF_CUDA(cudaEventRecord(c.ev1, c.stream));
+  PCF_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * k, cudaMemcpyDeviceToHost, c.stream));
+  int hflag = 0;
+  PCF_CUDA(cudaMemcpyAsync(&hflag, c.d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  PCF_CUDA(cudaStreamSynchronize(c.stream));
+  for (int i = 0; i < k; ++i) host_vals[i] = c.h_out[i];
+  float ms = 0.f;
+  PCF_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+  *seconds_kernel = ms * 1e-3;
+  *flag = hflag;
+  if (hflag) PCF_CUDA(cudaMemsetAsync(c.d_flag, 0, sizeof(int), c.stream));
+  return PCF_OK;
+}
+
+struct CallOut {
+  double vals[8] = {0};
+  double seconds_kernel = 0;
+  int launches = 0;
+  int flag = 0;
+};
+
+static int check_common(const pcf_params* p, pcf_result* out) {
+  if (!p || !out) return PCF_EINVAL;
+  std::memset(out, 0, sizeof(*out));
+  if (p->cp != 1 && p->cp != -1) return PCF_EINVAL_PAYOFF;
+  if (p->N <= 0) return PCF_EINVAL;
+  if (g_ctx.empty()) return PCF_ENOINIT;
+  return PCF_OK;
+}
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static void fill_mc_result(pcf_result* out, const std::vector<CallOut>& co, double disc, long long n,
+                           long long units, double t0) {
+  out->sum = co[0].vals[0];
+  out->sumsq = co[0].vals[1];
+  out->n = n;
+  out->units = units;
+  out->price = (disc * out->sum) / (double)n;
+  double mean = out->sum / (double)n, var = out->sumsq / (double)n - mean * mean;
+  out->std_error = (n > 1 && var > 0) ? disc * std::sqrt(var / (double)(n - 1)) : 0.0;
+  for (auto& c : co) {
+    if (c.seconds_kernel > out->seconds_kernel) out->seconds_kernel = c.seconds_kernel;
+    out->launches += c.launches;
+  }
+  out->gpus = g_ctx[0].world;
+  out->seconds_total = now_s() - t0;
+}
+
+}  // namespace pcf
+
+using namespace pcf;
+
+// ================================================================================================
+extern "C" {
+
+int pcf_init(int gpus) {
+  if (!g_ctx.empty()) return PCF_OK;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_last_error(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    return PCF_ECUDA;
+  }
+  if (gpus <= 0 || gpus > ndev) gpus = (gpus <= 0) ? ndev : ndev;
+  g_ctx.resize(gpus);
+  for (int i = 0; i < gpus; ++i) {
+    int s = ctx_open(g_ctx[i], i, i, gpus);
+    if (s != PCF_OK) { pcf_shutdown(); return s; }
+  }
+  if (gpus > 1) {
+    int s = nccl_load();
+    if (s != PCF_OK) { pcf_shutdown(); return s; }
+    std::vector<void*> comms(gpus);
+    std::vector<int> devs(gpus);
+    for (int i = 0; i < gpus; ++i) devs[i] = i;
+    int r = g_nccl.CommInitAll(comms.data(), gpus, devs.data());
+    if (r != 0) {
+      set_last_error(std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r));
+      pcf_shutdown();
+      return PCF_ENCCL;
+    }
+    for (int i = 0; i < gpus; ++i) g_ctx[i].comm = comms[i];
+  }
+  return PCF_OK;
+}
+
+int pcf_nccl_unique_id(unsigned char id[128]) {
+  PCF_TRY(nccl_load());
+  NcclId nid;
+  PCF_NCCL(g_nccl.GetUniqueId(&nid));
+  std::memcpy(id, nid.internal, 128);
+  return PCF_OK;
+}
+
+int pcf_init_rank(int rank, int world, int device, const unsigned char* nccl_id) {
+  if (!g_ctx.empty()) return PCF_OK;
+  if (world < 1 || rank < 0 || rank >= world) return PCF_EINVAL;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_last_error(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    return PCF_ECUDA;
+  }
+  g_ctx.resize(1);
+  int s = ctx_open(g_ctx[0], device, rank, world);
+  if (s != PCF_OK) { pcf_shutdown(); return s; }
+  if (world > 1) {
+    if (!nccl_id) { pcf_shutdown(); return PCF_EINVAL; }
+    s = nccl_load();
+    if (s != PCF_OK) { pcf_shutdown(); return s; }
+    NcclId nid;
+    std::memcpy(nid.internal, nccl_id, 128);
+    int r = g_nccl.CommInitRank(&g_ctx[0].comm, world, nid, rank);
+    if (r != 0) {
+      set_last_error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+      pcf_shutdown();
+      return PCF_ENCCL;
+    }
+  }
+  return PCF_OK;
+}
+
+int pcf_shutdown(void) {
+  for (auto& c : g_ctx) ctx_close(c);
+  g_ctx.clear();
+  return PCF_OK;
+}
+
+int pcf_world_size(void) { return g_ctx.empty() ? 0 : g_ctx[0].world; }
+
+// ------------------------------------------------------------------------------------------------
+int pcf_mc_eur(const pcf_params* p, pcf_result* out) {
+  int s = check_common(p, out);
+  if (s == PCF_OK && p->replay && p->replay_len < p->N) s = PCF_EINVAL;
+  if (s != PCF_OK) { if (out) out->status = s; return s; }
+  const double t0 = now_s();
+  const long long pairs = (p->N + 1) / 2;
+  std::vector<CallOut> co(g_ctx.size());
+  s = for_each_ctx([&](Ctx& c) -> int {
+    CallOut& o = co[&c - &g_ctx[0]];
+    c.launches = 0;
+    Shard sh = shard_of(pairs, c.rank, c.world);
+    const double* d_rep = nullptr;
+    if (p->replay) {
+      long long off = 2 * sh.begin, end = std::min(p->N, 2 * sh.end);
+      PCF_TRY(upload_replay(c, p->replay, off, end - off, 0, &d_rep));
+    }
+    PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+    PCF_TRY(run_mc_eur(c, *p, sh, d_rep));
+    PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+    o.launches = c.launches;
+    return PCF_OK;
+  });
+  if (s == PCF_OK) fill_mc_result(out, co, std::exp(-p->r * p->T), p->N, p->N, t0);
+  out->status = s;
+  return s;
+}
+
+int pcf_mc_asia(const pcf_params* p, pcf_result* out) {
+  int s = check_common(p, out);
+  if (s == PCF_OK && p->M <= 0) s = PCF_EINVAL;
+  if (s == PCF_OK && p->replay && p->replay_len < p->N * (long long)p->M) s = PCF_EINVAL;
+  if (s != PCF_OK) { if (out) out->status = s; return s; }
+  const double t0 = now_s();
+  std::vector<CallOut> co(g_ctx.size());
+  s = for_each_ctx([&](Ctx& c) -> int {
+    CallOut& o = co[&c - &g_ctx[0]];
+    c.launches = 0;
+    Shard sh = shard_of(p->N, c.rank, c.world);
+    const double* d_rep = nullptr;
+    if (p->replay) PCF_TRY(upload_replay(c, p->replay, sh.begin * p->M, sh.size() * p->M, 0, &d_rep));
+    PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+    PCF_TRY(run_mc_asia(c, *p, sh, d_rep));
+    PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+    o.launches = c.launches;
+    return PCF_OK;
+  });
+  if (s == PCF_OK) fill_mc_result(out, co, std::exp(-p->r * p->T), p->N, p->N * (long long)p->M, t0);
+  out->status = s;
+  return s;
+}
+
+int pcf_chol_equicorr(int d, double rho, double* L) {
+  if (d < 1 || d > PCF_MAX_ASSETS || !L) return PCF_EINVAL;
+  // covar(i,j) = i==j ? 1 : rho  (reference include/mvn.h:55-60), row-by-row Cholesky (mvn.h:63-70)
+  std::memset(L, 0, sizeof(double) * d * d);
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = (i == j) ? 1.0 : rho;
+      for (int k = 0; k < j; ++k) s -= L[i * d + k] * L[j * d + k];
+      if (i == j) {
+        if (!(s > 0.0)) return PCF_ENOTPD;
+        L[i * d + i] = std::sqrt(s);
+      } else {
+        L[i * d + j] = s / L[j * d + j];
+      }
+    }
+  return PCF_OK;
+}
+
+int pcf_mc_eur_multi(const pcf_params* p, pcf_result* out) {
+  int s = check_common(p, out);
+  if (s == PCF_OK && (p->assets < 1 || p->assets > PCF_MAX_ASSETS)) s = PCF_EINVAL;
+  if (s == PCF_OK && p->replay && p->replay_len < p->N * (long long)p->assets) s = PCF_EINVAL;
+  double L[PCF_MAX_ASSETS * PCF_MAX_ASSETS];
+  if (s == PCF_OK) s = pcf_chol_equicorr(p->assets, p->rho, L);
+  if (s != PCF_OK) { if (out) out->status = s; return s; }
+  const double t0 = now_s();
+  std::vector<CallOut> co(g_ctx.size());
+  s = for_each_ctx([&](Ctx& c) -> int {
+    CallOut& o = co[&c - &g_ctx[0]];
+    c.launches = 0;
+    Shard sh = shard_of(p->N, c.rank, c.world);
+    const double* d_rep = nullptr;
+    if (p->replay)
+      PCF_TRY(upload_replay(c, p->replay, sh.begin * p->assets, sh.size() * p->assets, 0, &d_rep));
+    PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+    PCF_TRY(run_mc_basket(c, *p, L, sh, d_rep));
+    PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+    o.launches = c.launches;
+    return PCF_OK;
+  });
+  if (s == PCF_OK) fill_mc_result(out, co, std::exp(-p->r * p->T), p->N, p->N, t0);
+  out->status = s;
+  return s;
+}
+
+int pcf_mc_amer(const pcf_params* p, pcf_result* out) {
+  int s = check_common(p, out);
+  if (s == PCF_OK && p->M <= 0) s = PCF_EINVAL;
+  if (s == PCF_OK && (p->N % 2) != 0) s = PCF_EODD_N;  // reference include/common.h:180
+  if (s == PCF_OK && p->replay && p->replay_len < (p->N / 2) * (long long)p->M) s = PCF_EINVAL;
+  if (s != PCF_OK) { if (out) out->status = s; return s; }
+  const double t0 = now_s();
+  const long long pairs = p->N / 2;
+  std::vector<CallOut> co(g_ctx.size());
+  s = for_each_ctx([&](Ctx& c) -> int {
+    CallOut& o = co[&c - &g_ctx[0]];
+    c.launches = 0;
+    Shard sh = shard_of(pairs, c.rank, c.world);
+    const size_t rep_bytes = p->replay ? (((size_t)sh.size() * p->M * 8 + 255) / 256) * 256 + 256 : 0;
+    PCF_TRY(ctx_reserve(c, rep_bytes + amer_workspace_bytes(sh.size(), p->M)));
+    const double* d_rep = nullptr;
+    if (p->replay) PCF_TRY(upload_replay(c, p->replay, sh.begin * p->M, sh.size() * p->M, 0, &d_rep));
+    PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+    PCF_TRY(run_mc_amer(c, *p, sh, d_rep, rep_bytes));
+    PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+    o.launches = c.launches;
+    return PCF_OK;
+  });
+  if (s == PCF_OK) {
+    for (auto& c : co)
+      if (c.flag) s = c.flag;  // PCF_ESINGULAR raised on the device
+  }
+  if (s == PCF_OK) {
+    fill_mc_result(out, co, 1.0, p->N, p->N * (long long)p->M, t0);
+    // mc_amer.cpp:113: floored at the immediate-exercise value
+    out->price = std::max(payoff(p->S0, p->E, p->cp), out->sum / (double)p->N);
+  }
+  out->status = s;
+  return s;
+}
+
+int pcf_binom_embar(const pcf_params* p, pcf_result* out) {
+  int s = check_common(p, out);
+  if (s == PCF_OK && p->N > 2147483647LL) s = PCF_EINVAL;  // reference N is an int
+  if (s != PCF_OK) { if (out) out->status = s; return s; }
+  const double t0 = now_s();
+  const long long until = (p->N % 2 != 0) ? (p->N + 1) / 2 : p->N / 2;  // binom_embar.cpp:31-33
+  long long lo = 0;
+  if (p->flags & PCF_FLAG_BINOM_WINDOW) {
+    // Hoeffding: P(|X - Np| >= t) <= 2 exp(-2 t^2 / N); a term below 2^-1075 is exactly 0 in FP64.
+    // Pairs (i, N-i) with i < min(Np, Nq) - W carry only such terms.
+    double u, d, pp, q;
+    binom_lattice(p->r, p->sigma, p->T, p->N, u, d, pp, q);
+    double W = 19.4 * std::sqrt((double)p->N) + 2.0;
+    double m = std::min(pp, q) * (double)p->N - W;
+    if (m > 0) lo = std::min((long long)m, until);
+  }
+  std::vector<CallOut> co(g_ctx.size());
+  s = for_each_ctx([&](Ctx& c) -> int {
+    CallOut& o = co[&c - &g_ctx[0]];
+    c.launches = 0;
+    Shard sh = shard_of(until - lo, c.rank, c.world);
+    sh.begin += lo; sh.end += lo;
+    PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+    PCF_TRY(run_binom(c, *p, sh, (p->N % 2 == 0) && c.rank == 0));
+    PCF_TRY(finish_call(c, 1, o.vals, &o.seconds_kernel, &o.flag));
+    o.launches = c.launches;
+    return PCF_OK;
+  });
+  if (s == PCF_OK) {
+    out->sum = co[0].vals[0];
+    out->price = std::exp(-p->r * p->T) * out->sum;  // binom_embar.cpp:49
+    out->n = p->N + 1;
+    out->units = p->N + 1;
+    for (auto& c : co) {
+      if (c.seconds_kernel > out->seconds_kernel) out->seconds_kernel = c.seconds_kernel;
+      out->launches += c.launches;
+    }
+    out->gpus = g_ctx[0].world;
+    out->seconds_total = now_s() - t0;
+  }
+  out->status = s;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+int pcf_normal_stream(unsigned long long seed, unsigned int stream, unsigned long long index0,
+                      long long count, int T, double scale, double* out_host) {
+  if (g_ctx.empty()) return PCF_ENOINIT;
+  if (count < 0 || T <= 0 || !out_host) return PCF_EINVAL;
+  Ctx& c = g_ctx[0];
+  PCF_CUDA(cudaSetDevice(c.device));
+  size_t bytes = (size_t)count * T * sizeof(double);
+  double* d = nullptr;
+  PCF_CUDA(cudaMalloc(&d, bytes ? bytes : 8));
+  int s = run_normal_stream(c, seed, stream, index0, count, T, scale, d);
+  if (s == PCF_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_host, d, bytes, cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); s = PCF_ECUDA; }
+  }
+  cudaFree(d);
+  return s;
+}
+
+int pcf_philox4x32_10(const unsigned int ctr[4], const unsigned int key[2], unsigned int out[4]) {
+  if (g_ctx.empty()) return PCF_ENOINIT;
+  Ctx& c = g_ctx[0];
+  PCF_CUDA(cudaSetDevice(c.device));
+  uint32_t* d = (uint32_t*)(c.d_out + 32);
+  PCF_TRY(run_philox_kat(c, ctr, key, d));
+  PCF_CUDA(cudaMemcpyAsync(out, d, 16, cudaMemcpyDeviceToHost, c.stream));
+  PCF_CUDA(cudaStreamSynchronize(c.stream));
+  return PCF_OK;
+}
+
+int pcf_fp64_peak(double seconds_target, double* dfma_per_sec) {
+  if (g_ctx.empty()) return PCF_ENOINIT;
+  PCF_CUDA(cudaSetDevice(g_ctx[0].device));
+  return run_fp64_peak(g_ctx[0], seconds_target, dfma_per_sec);
+}
+
+int pcf_hbm_peak(long long bytes, double* bytes_per_sec) {
+  if (g_ctx.empty()) return PCF_ENOINIT;
+  PCF_CUDA(cudaSetDevice(g_ctx[0].device));
+  return run_hbm_peak(g_ctx[0], bytes, bytes_per_sec);
+}
+
+int pcf_device_info(char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor,
+                    long long* mem_bytes) {
+  int dev = g_ctx.empty() ? 0 : g_ctx[0].device;
+  cudaDeviceProp prop;
+  PCF_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (name && name_len > 0) {
+    std::strncpy(name, prop.name, (size_t)name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (mem_bytes) *mem_bytes = (long long)prop.totalGlobalMem;
+  return PCF_OK;
+}
+
+const char* pcf_strerror(int status) {
+  switch (status) {
+    case PCF_OK: return "ok";
+    case PCF_EINVAL_PAYOFF: return "Unknown payoff function";
+    case PCF_EODD_N: return "N needs to be divisible by 2 for finding paths";
+    case PCF_ESINGULAR: return "Detereminant is not > 0";
+    case PCF_EINVAL: return "invalid argument";
+    case PCF_ENOTPD: return "correlation matrix is not positive definite";
+    case PCF_ECUDA: return "CUDA failure (no device, or runtime error)";
+    case PCF_ENCCL: return "NCCL failure";
+    case PCF_ENOINIT: return "pcf_init() has not been called";
+    case PCF_ENOMEM: return "device memory allocation failed";
+    default: return "unknown status";
+  }
+}
+
+const char* pcf_last_error(void) {
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  copy = g_last_error;
+  return copy.c_str();
+}
+
+}  // extern "C"
