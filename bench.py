@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- simulated path-steps per second of the Monte Carlo hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU)
+
+A "step" is one pass of the hot path over one batch of synthetic parameters: one C-ABI call pricing the
+whole workload (default: BASELINE.json config 3, mc_asia call 100/100/.05/.2/1, 1e9 paths x 252 dates,
+split over the N GPUs by path index -- strong scaling, Philox keyed by global path index).
+
+  value   path-steps/s from CUDA-event time on the launching stream (kernel + all-reduce), max over ranks
+  e2e     same metric from the host wall clock around the C-ABI calls (parameter upload, launch, result
+          read-back all inside), barrier + device sync on both sides, max over ranks
+  roofline  algorithmic FP64-pipe slots (55 per path-step) / kernel time, against the DFMA
+          issue peak measured in this run by a register-resident FMA-chain kernel (MEASURED_PEAKS.json
+          has no FP64 figure)
+  cpu_baseline  the reference's own OpenMP program (oracle/_ref/mc_asia_omp, compiled from the unmodified
+          sources) on this box's host cores, bounded sample
+  others  the other four BASELINE.json configs, one short measurement each, same definitions
+
+`--impl reference` times the reference's CPU implementation (rank 0 only) on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P = dict(S0=100.0, E=100.0, r=0.05, sigma=0.2, T=1.0)
+SEED0 = 20240229
+
+# algorithmic work per unit. FP64 "slots" = DFMA/DMUL/DADD issue slots; FMA-equivalent
+# flops = 2 x slots.
+WORKLOADS = {
+    "mc_asia": dict(config="mc_asia call 100/100/.05/.2/1, 1e9 paths x 252 dates (BASELINE config 3)",
+                    N=1_000_000_000, M=252, steps_per_unit=252, slots=55.0, bound="fp64", unit="path-steps/s",
+                    kernel="mc_asia_kernel"),
+    "mc_eur": dict(config="mc_eur call 100/100/.05/.2/1, 2e9 paths (config 1 at the size SURVEY 8d quotes the "
+                          "roofline on; 1e7 paths is 30 us of work)",
+                   N=2_000_000_000, M=0, steps_per_unit=1, slots=60.0, bound="fp64", unit="path-steps/s",
+                   kernel="mc_eur_kernel"),
+    "mc_eur_multi": dict(config="mc_eur_multi call, d=16 rho=0.5, 1e9 paths (BASELINE config 4)",
+                         N=1_000_000_000, M=0, steps_per_unit=1, slots=990.0, bound="fp64", unit="path-steps/s",
+                         kernel="mc_basket_kernel", assets=16, rho=0.5),
+    "mc_amer": dict(config="mc_amer put, 1e8 paths x 50 exercise dates, paths in HBM (BASELINE config 5)",
+                    N=100_000_000, M=50, steps_per_unit=50, bytes=36.0, bound="hbm", unit="path-steps/s",
+                    kernel="amer_paths_kernel+amer_moments_kernel+amer_decide_kernel"),
+    "binom_embar": dict(config="binom_embar call 100/100/.05/.2/1, N=1e8 steps (BASELINE config 2)",
+                        N=100_000_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
+                        kernel="binom_terms_kernel"),
+}
+
+
+def run_ours_once(pcf, name, seed, N=None):
+    w = WORKLOADS[name]
+    N = N or w["N"]
+    a = (P["S0"], P["E"], P["r"], P["sigma"], P["T"])
+    if name == "mc_asia":
+        return pcf.mc_asia(*a, N, w["M"], "call", seed=seed)
+    if name == "mc_eur":
+        return pcf.mc_eur(*a, N, "call", seed=seed)
+    if name == "mc_eur_multi":
+        return pcf.mc_eur_multi(*a, N, "call", w["assets"], w["rho"], seed=seed)
+    if name == "mc_amer":
+        return pcf.mc_amer(*a, N, w["M"], "put", seed=seed)
+    if name == "binom_embar":
+        return pcf.binom(*a, N, "call")
+    raise KeyError(name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ts, line in self.lines:
+            if not (t0 <= ts <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(pw), "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_asia(n_paths, threads, seed=SEED0):
+    """Times the reference's CPU implementation of the headline workload on `threads` host threads.
+    Returns (path_steps_per_s, kind, seconds). kind = "reference" (oracle/_ref/mc_asia_omp, the unmodified
+    source at -O2, its own T_calculation clock) or "port" (oracle/cpu_ref.cpp twin) when _ref is absent."""
+    import oracle
+    M = WORKLOADS["mc_asia"]["M"]
+    if oracle.have_ref():
+        row = oracle.ref_row("mc_asia_omp", "call", 100, 100, 0.05, 0.2, 1, n_paths, M, threads)
+        sec = float(row[12])
+        return n_paths * M / sec, "reference", sec
+    oracle.mc_asia_omp_timed(100, 100, .05, .2, 1, 20000, M, "call", seed, threads)  # wake the thread pool
+    _, sec = oracle.mc_asia_omp_timed(100, 100, .05, .2, 1, n_paths, M, "call", seed, threads)
+    return n_paths * M / sec, "port", sec
+
+
+def bench_reference(args, rank):
+    """--impl reference: rank 0 alone times the reference's CPU path; other ranks exit 0 without work."""
+    if rank != 0:
+        return
+    threads = host_threads()
+    w = WORKLOADS["mc_asia"]
+    n_paths = args.ref_paths
+    for _ in range(args.warmup):
+        cpu_reference_asia(max(n_paths // 8, 1000), threads)
+    secs, kind = [], "reference"
+    for _ in range(args.steps):
+        _, kind, sec = cpu_reference_asia(n_paths, threads)
+        secs.append(sec)
+    value = n_paths * w["M"] * args.steps / sum(secs)
+    sample = (f"{n_paths} of 1e9 paths x {w['M']} dates per step (oracle/_ref/mc_asia_omp -O2, unmodified reference "
+              f"source, {threads} OpenMP threads)" if kind == "reference" else
+              f"{n_paths} of 1e9 paths x {w['M']} dates per step (oracle/cpu_ref.cpp OpenMP twin, {threads} threads)")
+    print(json.dumps({
+        "impl": "reference", "metric": "path_steps_per_sec", "value": value, "unit": "path-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(secs) / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["config"], "sample_paths_per_step": n_paths},
+        "cpu_baseline": {"value": value, "unit": "path-steps/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def measure(pcf, dist, job, name, steps, warmup, N=None):
+    """K timed steps of one workload. Returns dict(device_s, wall_s, launches, units, price, se)."""
+    import torch
+    for i in range(warmup):
+        run_ours_once(pcf, name, SEED0 + 1000 + i, N)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dist.barrier(job)
+    t0 = time.perf_counter()
+    dev, launches, last = [], 0, None
+    for i in range(steps):
+        last = run_ours_once(pcf, name, SEED0 + i, N)   # synchronous: returns after the result is on the host
+        dev.append(last.seconds_kernel)
+        launches += last.launches
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dist.barrier(job)
+    wall = time.perf_counter() - t0
+    # max over ranks, per step for the device clock and once for the wall clock
+    red = dist.reduce_scalars(job, dev + [wall], "max")
+    tot_launch = dist.reduce_scalars(job, [float(launches)], "sum")[0]
+    return dict(device_s=sum(red[:-1]), wall_s=red[-1], launches=int(tot_launch), units=last.units,
+                price=last.price, se=last.std_error, t0=t0)
+
+
+def roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src):
+    w = WORKLOADS[name]
+    if w["bound"] == "fp64":
+        ach = units_per_s * w["slots"] * 2 / 1e12
+        peak = fp64_dfma_per_s * 2 / 1e12
+        return {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "kernel": w["kernel"], "algorithmic": f"{w['slots']:g} FP64 issue slots per unit (SURVEY 8d), FMA = 2 flop",
+                "peak_source": "measured in this run: DFMA-chain microbenchmark (pcf_fp64_peak); MEASURED_PEAKS.json has no FP64 figure"}
+    ach = units_per_s * w["bytes"] / 1e9
+    peak = hbm_bytes_per_s / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "kernel": w["kernel"], "algorithmic": f"{w['bytes']:g} B per path-step (SURVEY 8d: 8 B path write + 28 B sweep)",
+            "peak_source": hbm_src}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mc_asia", choices=sorted(WORKLOADS))
+    ap.add_argument("--paths", type=int, default=0, help="override the workload's path count (debug)")
+    ap.add_argument("--ref-paths", type=int, default=2_000_000, help="--impl reference: paths per step (bounded sample)")
+    ap.add_argument("--cpu-paths", type=int, default=12_000_000, help="cpu_baseline sample (paths)")
+    ap.add_argument("--no-others", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    from parcompfin_b200 import dist
+    rank, world, local = dist.env_job()
+    if args.impl == "reference":
+        bench_reference(args, rank)
+        return
+
+    import torch
+    import parcompfin_b200 as pcf
+    pcf.load_library()  # fails loudly when the CUDA extension is missing: there is no fallback
+    job = dist.setup()
+    if job.world > 1:
+        dist.init_library(job)
+    else:
+        pcf.init(args.gpus)  # single process: N GPUs driven in-process (N = 1 in the default run)
+    n_gpus = pcf.world_size()
+
+    name = args.workload
+    w = WORKLOADS[name]
+    sampler = ClockSampler(local) if job.rank == 0 else None
+    if sampler:
+        sampler.start()
+    t_wall0 = time.time()
+    m = measure(pcf, dist, job, name, args.steps, args.warmup, args.paths or None)
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    total_units = m["units"] * args.steps
+    value = total_units / m["device_s"]
+    e2e = total_units / m["wall_s"]
+
+    # roofline denominators, measured on this GPU right after the timed region
+    fp64_peak = pcf.fp64_peak(0.25)
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        hbm = json.load(open(peaks_file))["hbm_gbs"] * 1e9
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        hbm, hbm_src = 6.65e12, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+    others = []
+    if not args.no_others:
+        for other in WORKLOADS:
+            if other == name:
+                continue
+            try:
+                mo = measure(pcf, dist, job, other, 2, 3)
+                ups = mo["units"] * 2 / mo["device_s"]
+                others.append({"workload": WORKLOADS[other]["config"], "value": ups, "unit": WORKLOADS[other]["unit"],
+                               "e2e": mo["units"] * 2 / mo["wall_s"], "ms_per_step": 1e3 * mo["device_s"] / 2,
+                               "price": mo["price"], "std_error": mo["se"], "gpu_launches": mo["launches"],
+                               "roofline": roofline_for(other, ups / n_gpus, fp64_peak, hbm, hbm_src)})
+            except Exception as ex:  # e.g. the path store does not fit
+                others.append({"workload": WORKLOADS[other]["config"], "error": str(ex)})
+
+    cpu = None
+    if job.rank == 0 and n_gpus == 1 and not args.no_cpu:
+        threads = host_threads()
+        v, kind, sec = cpu_reference_asia(args.cpu_paths, threads)
+        cpu = {"value": v, "unit": "path-steps/s", "cores": threads, "kind": kind,
+               "sample": f"{args.cpu_paths} of 1e9 paths x 252 dates, {sec:.1f} s, mc_asia_omp "
+                         + ("(unmodified reference source, -O2)" if kind == "reference" else "(oracle port)")}
+
+    if job.rank == 0:
+        line = {
+            "metric": "path_steps_per_sec", "value": value, "unit": w["unit"], "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * m["device_s"] / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["config"], "paths": args.paths or w["N"], "dates": w["M"],
+                       "parallelism": f"paths sharded by global index over {n_gpus} GPU(s)",
+                       "l2": "no input arrays: the kernel reads no global memory (parameters only), nothing to flush; "
+                             "the mc_amer entry in `others` streams a 40 GB path store (>> 126 MB L2)",
+                       "price": m["price"], "std_error": m["se"]},
+            "e2e": {"value": e2e, "unit": w["unit"], "h2d_bytes_per_step": 104 * n_gpus, "d2h_bytes_per_step": 20 * n_gpus},
+            "gpu_launches": m["launches"],
+            "roofline": roofline_for(name, value / n_gpus, fp64_peak, hbm, hbm_src),
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "others": others,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier(job)
+    pcf.shutdown()
+    dist.teardown(job)
+
+
+if __name__ == "__main__":
+    main()

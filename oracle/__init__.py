@@ -48,6 +48,10 @@ def lib() -> ctypes.CDLL:
         L.oracle_mc_basket.argtypes = [_d] * 5 + [_ll, _i, _i, _d, _P, _P, _P, ctypes.POINTER(_i)]
         L.oracle_mc_basket_omp_timed.restype = _d
         L.oracle_mc_basket_omp_timed.argtypes = [_d] * 5 + [_ll, _i, _i, _d, _u64, _i, _P]
+        L.oracle_mc_asia_omp_timed.restype = _d
+        L.oracle_mc_asia_omp_timed.argtypes = [_d] * 5 + [_ll, _i, _i, _u64, _i, _P]
+        L.oracle_mc_eur_omp_timed.restype = _d
+        L.oracle_mc_eur_omp_timed.argtypes = [_d] * 5 + [_ll, _i, _u64, _i, _P]
         L.oracle_binom_params.argtypes = [_d, _d, _d, _i, _P, _P, _P, _P]
         L.oracle_binom.restype = _d
         L.oracle_binom.argtypes = [_d] * 5 + [_i, _i, _i]
@@ -126,6 +130,18 @@ def mc_basket_omp_timed(S0, E, r, sigma, T, N, payoff_fun, d, rho, seed, threads
     sec = _d()
     price = lib().oracle_mc_basket_omp_timed(S0, E, r, sigma, T, N, _cp(payoff_fun), d, rho, seed, threads,
                                              ctypes.byref(sec))
+    return price, sec.value
+
+
+def mc_asia_omp_timed(S0, E, r, sigma, T, N, M, payoff_fun, seed, threads):
+    sec = _d()
+    price = lib().oracle_mc_asia_omp_timed(S0, E, r, sigma, T, N, M, _cp(payoff_fun), seed, threads, ctypes.byref(sec))
+    return price, sec.value
+
+
+def mc_eur_omp_timed(S0, E, r, sigma, T, N, payoff_fun, seed, threads):
+    sec = _d()
+    price = lib().oracle_mc_eur_omp_timed(S0, E, r, sigma, T, N, _cp(payoff_fun), seed, threads, ctypes.byref(sec))
     return price, sec.value
 
 

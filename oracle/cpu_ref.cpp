@@ -393,3 +393,54 @@ ORACLE_API void oracle_normal_stream(uint64_t seed, uint32_t stream, uint64_t in
       if (t + 1 < T) out[i * (long long)T + t + 1] = scale * zo;
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Timing-only OpenMP twins ("port" CPU baseline, used when oracle/_ref is not available). Same
+// structure as reference src/mc_asia_omp.cpp:18-47 / src/mc_eur_omp.cpp:16-33: one mt19937 +
+// normal_distribution per thread seeded seed*(1+thread), `omp for schedule(dynamic,1000)
+// reduction(+)`. Returns the price; *seconds = wall time of the pricing function.
+ORACLE_API double oracle_mc_asia_omp_timed(double S0, double E, double r, double sigma, double T,
+                                           long long N, int M, int cp, uint64_t seed, int threads,
+                                           double* seconds) {
+  omp_set_num_threads(threads);
+  double t0 = omp_get_wtime();
+  double result = 0;
+#pragma omp parallel
+  {
+    const double dt = (double)T / (double)M;
+    std::mt19937 gen;
+    gen.seed((std::mt19937::result_type)(seed * (1 + omp_get_thread_num())));
+    std::normal_distribution<> norm{0, std::sqrt(dt)};
+#pragma omp for nowait schedule(dynamic, 1000) reduction(+ : result)
+    for (long long n = 0; n < N; ++n) {
+      double St = S0, I = 0;
+      for (int m = 0; m < M; ++m) {
+        double dBi = norm(gen);
+        I += St * (1 + r * dt / 2 + sigma * dBi / 2);
+        St *= std::exp((r - sigma * sigma / 2) * dt + sigma * dBi);
+      }
+      result += payoff(I / (double)M, E, cp);
+    }
+  }
+  *seconds = omp_get_wtime() - t0;
+  return (std::exp(-r * T) * result) / (double)N;
+}
+
+ORACLE_API double oracle_mc_eur_omp_timed(double S0, double E, double r, double sigma, double T,
+                                          long long N, int cp, uint64_t seed, int threads,
+                                          double* seconds) {
+  omp_set_num_threads(threads);
+  double t0 = omp_get_wtime();
+  double result = 0;
+#pragma omp parallel
+  {
+    std::mt19937 gen;
+    gen.seed((std::mt19937::result_type)(seed * (1 + omp_get_thread_num())));
+    std::normal_distribution<> norm{0, std::sqrt(T)};
+#pragma omp for nowait schedule(dynamic, 1000) reduction(+ : result)
+    for (long long n = 0; n < N; ++n)
+      result += payoff(S0 * std::exp((r - sigma * sigma / 2) * T + sigma * norm(gen)), E, cp);
+  }
+  *seconds = omp_get_wtime() - t0;
+  return (std::exp(-r * T) * result) / (double)N;
+}

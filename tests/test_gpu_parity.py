@@ -1,0 +1,290 @@
+"""GPU parity tests (-m gpu): libpcf.so through its C ABI against the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star):
+  replay mode  -- same normal stream as the reference: 1e-12 relative (only summation order and
+                  last-ulp libm differences remain);
+  native mode  -- within 3 standard errors of the reference / Black-Scholes;
+  binomial sum -- 1e-10 relative against binom_embar, and 1e-12 against the exact sum.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+REPLAY_TOL = 1e-12
+BINOM_TOL = 1e-10
+BS_CALL = 10.450583572185565
+BS_PUT = 5.573526022256971
+P1 = (100, 100, 0.05, 0.2, 1)
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+# ---------------------------------------------------------------------------------------------------
+# generator
+def test_philox_known_answers_on_device(gpu):
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert gpu.philox4x32_10(ctr, key) == want
+
+
+def test_normal_stream_matches_cpu_restatement(gpu):
+    for seed, stream, i0, cnt, T in [(7, 1, 1000, 4096, 5), (2 ** 40 + 3, 3, 2 ** 33, 1000, 50), (0, 0, 0, 1, 1)]:
+        g = gpu.normal_stream(seed, stream, i0, cnt, T, 0.5)
+        o = oracle.normal_stream(seed, stream, i0, cnt, T, 0.5)
+        assert np.abs(g - o).max() < 5e-15
+
+
+def test_normal_stream_distribution(gpu):
+    z = gpu.normal_stream(99, 1, 0, 200000, 20).reshape(-1)
+    n = z.size
+    assert abs(z.mean()) < 4 / math.sqrt(n)
+    assert abs(z.var() - 1) < 4 * math.sqrt(2 / n)
+    assert abs((z ** 3).mean()) < 4 * math.sqrt(15 / n)
+    assert abs((z ** 4).mean() - 3) < 4 * math.sqrt(96 / n)
+    # tail mass beyond 3 sigma
+    p3 = 2 * 0.0013498980316301
+    assert abs((np.abs(z) > 3).mean() - p3) < 4 * math.sqrt(p3 / n)
+
+
+# ---------------------------------------------------------------------------------------------------
+# replay parity against the compiled reference's outputs (golden) and against the oracle
+def test_mc_eur_replay_golden(gpu, golden):
+    for c in golden["reference_vectors"]["mc_eur"]:
+        S0, E, r, sigma, T = c["params"]
+        w = oracle.normals_mt19937(c["seed"], math.sqrt(T), c["N"])
+        g = gpu.mc_eur(S0, E, r, sigma, T, c["N"], c["payoff"], replay=w)
+        assert rel(g.price, c["price"]) < REPLAY_TOL, c
+        assert g.n == c["N"] and g.units == c["N"] and g.launches >= 1
+
+
+def test_mc_asia_replay_golden(gpu, golden):
+    for c in golden["reference_vectors"]["mc_asia"]:
+        S0, E, r, sigma, T = c["params"]
+        w = oracle.normals_mt19937(c["seed"], math.sqrt(T / c["M"]), c["N"] * c["M"])
+        g = gpu.mc_asia(S0, E, r, sigma, T, c["N"], c["M"], c["payoff"], replay=w)
+        assert rel(g.price, c["price"]) < REPLAY_TOL, c
+        assert g.units == c["N"] * c["M"]
+
+
+def test_mc_amer_replay_golden(gpu, golden):
+    for c in golden["reference_vectors"]["mc_amer"]:
+        S0, E, r, sigma, T = c["params"]
+        w = oracle.normals_mt19937(c["seed"], math.sqrt(T / c["M"]), c["N"] // 2 * c["M"])
+        g = gpu.mc_amer(S0, E, r, sigma, T, c["N"], c["M"], c["payoff"], replay=w)
+        assert rel(g.price, c["price"]) < REPLAY_TOL, c
+        assert g.launches == 2 + 2 * (c["M"] - 1)  # paths + (moments, decide) per date + final
+
+
+def test_mc_amer_few_itm_branches(gpu):
+    # deep out-of-the-money call: most dates have 0, 1 or 2 paths in the money (mc_amer.cpp:73-83)
+    for seed, N, M, E in [(6, 2000, 20, 160), (8, 500, 30, 150), (9, 64, 40, 135)]:
+        w = oracle.normals_mt19937(seed, math.sqrt(1 / M), N // 2 * M)
+        o = oracle.mc_amer(100, E, .05, .2, 1, N, M, "call", w)
+        g = gpu.mc_amer(100, E, .05, .2, 1, N, M, "call", replay=w)
+        assert rel(g.price, o) < REPLAY_TOL or abs(g.price - o) < 1e-15
+
+
+def test_basket_replay_vs_oracle(gpu):
+    for d, rho, N, pf in [(16, 0.5, 50000, "call"), (4, 0.5, 30000, "call"), (3, 0.2, 10001, "put"), (1, 0.0, 5000, "call"),
+                          (32, 0.9, 4000, "put"), (7, -0.1, 3000, "call")]:
+        Z = oracle.normals_mt19937(42 + d, 1.0, N * d)
+        o = oracle.mc_basket(100, 100, .05, .2, 1, N, pf, d, rho, Z)
+        g = gpu.mc_eur_multi(100, 100, .05, .2, 1, N, pf, d, rho, replay=Z)
+        assert rel(g.price, o) < REPLAY_TOL, (d, rho)
+
+
+def test_basket_cholesky_matches_oracle(gpu):
+    for d, rho in [(16, 0.5), (32, 0.99), (5, -0.2)]:
+        assert np.abs(gpu.chol_equicorr(d, rho) - oracle.chol_equicorr(d, rho)).max() < 1e-15
+
+
+# ---------------------------------------------------------------------------------------------------
+# native mode: the oracle fed the kernels' own Philox normals must reproduce the GPU price
+def test_native_equals_oracle_on_dumped_stream(gpu):
+    seed = 5
+    N = 100001
+    z = gpu.normal_stream(seed, gpu.STREAM_EUR, 0, (N + 1) // 2, 2).reshape(-1)[:N]
+    assert rel(gpu.mc_eur(*P1, N, "put", seed=seed).price, oracle.mc_eur(*P1, N, "put", z)) < REPLAY_TOL
+    N, M = 5000, 253  # odd M: last Philox block half used
+    z = gpu.normal_stream(seed, gpu.STREAM_ASIA, 0, N, M, math.sqrt(1 / M))
+    assert rel(gpu.mc_asia(*P1, N, M, "call", seed=seed).price, oracle.mc_asia(*P1, N, M, "call", z)) < REPLAY_TOL
+    N, d = 20000, 16
+    z = gpu.normal_stream(seed, gpu.STREAM_BASKET, 0, N, d)
+    assert rel(gpu.mc_eur_multi(*P1, N, "call", d, 0.5, seed=seed).price,
+               oracle.mc_basket(*P1, N, "call", d, 0.5, z)) < REPLAY_TOL
+    N, M = 20000, 50
+    z = gpu.normal_stream(seed, gpu.STREAM_AMER, 0, N // 2, M, math.sqrt(1 / M))
+    assert rel(gpu.mc_amer(*P1, N, M, "put", seed=seed).price, oracle.mc_amer(*P1, N, M, "put", z)) < REPLAY_TOL
+    N, M = 6000, 7
+    z = gpu.normal_stream(seed, gpu.STREAM_AMER, 0, N // 2, M, math.sqrt(1 / M))
+    assert rel(gpu.mc_amer(100, 110, .02, .75, 1, N, M, "call", seed=seed).price,
+               oracle.mc_amer(100, 110, .02, .75, 1, N, M, "call", z)) < REPLAY_TOL
+
+
+def test_native_within_three_standard_errors(gpu, golden):
+    g = gpu.mc_eur(*P1, 10_000_000, "call", seed=20240229)   # BASELINE config 1
+    assert abs(g.price - BS_CALL) < 3 * g.std_error and 0.003 < g.std_error < 0.006
+    g = gpu.mc_eur(*P1, 10_000_000, "put", seed=1)
+    assert abs(g.price - BS_PUT) < 3 * g.std_error
+    # Asian: against the reference's own run (golden, N=1e5 paths => its error bar dominates)
+    ref = [c for c in golden["reference_vectors"]["mc_asia"] if c["N"] == 100_000 and c["M"] == 252][0]
+    g = gpu.mc_asia(*P1, 4_000_000, 252, "call", seed=3)
+    se_ref = g.std_error * math.sqrt(4_000_000 / ref["N"])
+    assert abs(g.price - ref["price"]) < 3 * math.hypot(g.std_error, se_ref)
+    # American (reference's scheme): against the reference's own 1e6-path run
+    ref = [c for c in golden["reference_vectors"]["mc_amer"] if c["N"] == 1_000_000][0]
+    g = gpu.mc_amer(*P1, 4_000_000, 50, "put", seed=3)
+    se_ref = g.std_error * math.sqrt(4_000_000 / ref["N"])
+    assert abs(g.price - ref["price"]) < 3 * math.hypot(g.std_error, se_ref)
+    # basket: d = 1 is the European call; rho -> 1 collapses to Black-Scholes
+    g = gpu.mc_eur_multi(*P1, 4_000_000, "call", 1, 0.0, seed=4)
+    assert abs(g.price - BS_CALL) < 3 * g.std_error
+    g = gpu.mc_eur_multi(*P1, 2_000_000, "call", 16, 1 - 1e-12, seed=4)
+    assert abs(g.price - BS_CALL) < 3 * g.std_error
+    # published statistical pin, reference results/results_mc_eur_multi.csv (d=4, rho=.5, r=.1): 11.92
+    g = gpu.mc_eur_multi(100, 100, .1, .2, 1, 20_000_000, "call", 4, 0.5, seed=4)
+    assert abs(g.price - 11.92) < 3 * g.std_error + 0.01
+
+
+# ---------------------------------------------------------------------------------------------------
+# binomial term sum
+def test_binom_matches_reference_vectors(gpu, golden):
+    exact = {(c["payoff"], tuple(c["params"]), c["N"]): c["price"] for c in golden["exact_binom"]["cases"]}
+    for c in golden["reference_vectors"]["binom_embar"]:
+        S0, E, r, sigma, T = c["params"]
+        g = gpu.binom(S0, E, r, sigma, T, c["N"], c["payoff"])
+        assert g.units == c["N"] + 1
+        if c["N"] <= 32000:
+            assert rel(g.price, c["price"]) < BINOM_TOL, c
+        else:
+            # comb() re-sums up to N logarithms per term and the reference drifts away from the exact sum of
+            # its own lattice: 5.0e-10 at N = 64000, 1.2e-10 at N = 1e5 (tests/golden/
+            # exact_binom.json). Beyond 32000 steps the gate is the exact sum, and the distance to the
+            # reference must be the reference's own error.
+            ex = exact[(c["payoff"], tuple(float(x) for x in c["params"]), c["N"])]
+            assert rel(g.price, ex) < 1e-12, c
+            assert abs(rel(g.price, c["price"]) - rel(c["price"], ex)) < 1e-12, c
+
+
+def test_binom_matches_published_csv(gpu, golden):
+    for c in golden["reference_vectors"]["binom_embar_csv"]:
+        S0, E, r, sigma, T = c["params"]
+        g = gpu.binom(S0, E, r, sigma, T, c["N"], c["payoff"])
+        assert rel(g.price, c["price"]) < 2e-9, c  # printed with 10 significant digits
+
+
+def test_binom_matches_exact_sum(gpu, golden):
+    for c in golden["exact_binom"]["cases"]:
+        S0, E, r, sigma, T = c["params"]
+        g = gpu.binom(S0, E, r, sigma, T, c["N"], c["payoff"])
+        assert rel(g.price, c["price"]) < 1e-12, c
+        gw = gpu.binom(S0, E, r, sigma, T, c["N"], c["payoff"], window=True)
+        assert rel(gw.price, g.price) < 1e-14
+
+
+def test_binom_full_size_properties(gpu):
+    # BASELINE config 2 sizes: no NaN where the reference overflows, convergence to
+    # Black-Scholes at rate 1/N, put-call parity of the lattice (sum of weights == 1, E[S_N] == S0 e^{rT})
+    prev = None
+    for N in (10 ** 5, 10 ** 6, 10 ** 7, 10 ** 8, 2 ** 31 - 1):
+        c = gpu.binom(*P1, N, "call").price
+        p = gpu.binom(*P1, N, "put").price
+        assert math.isfinite(c) and math.isfinite(p)
+        assert abs(c - BS_CALL) < 2.0 / N + 2e-8
+        assert abs((c - p) - (100 - 100 * math.exp(-0.05))) < 1e-8
+        if prev is not None:
+            assert abs(c - BS_CALL) <= abs(prev - BS_CALL) + 1e-8
+        prev = c
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at larger sizes, edge cases, error behaviour
+def test_determinism_and_homogeneity(gpu):
+    a = gpu.mc_asia(*P1, 2_000_000, 252, "call", seed=11)
+    b = gpu.mc_asia(*P1, 2_000_000, 252, "call", seed=11)
+    assert a.price == b.price and a.sumsq == b.sumsq          # fixed reduction order
+    c = gpu.mc_asia(200, 200, 0.05, 0.2, 1, 2_000_000, 252, "call", seed=11)
+    assert rel(c.price, 2 * a.price) < 1e-12                  # payoff is homogeneous of degree 1 in (S0, E)
+    d = gpu.mc_asia(*P1, 2_000_000, 252, "call", seed=12)
+    assert d.price != a.price
+    e1 = gpu.mc_amer(*P1, 1_000_000, 50, "put", seed=11)
+    e2 = gpu.mc_amer(*P1, 1_000_000, 50, "put", seed=11)
+    assert e1.price == e2.price
+
+
+def test_put_call_parity_same_stream(gpu):
+    N = 5_000_000
+    c = gpu.mc_eur(*P1, N, "call", seed=21)
+    p = gpu.mc_eur(*P1, N, "put", seed=21)
+    f = gpu.mc_eur(100, 0.0, 0.05, 0.2, 1, N, "call", seed=21)   # discounted mean of S_T
+    assert rel(c.price - p.price, f.price - 100 * math.exp(-0.05)) < 1e-10
+
+
+def test_edge_cases(gpu):
+    # smallest inputs
+    w = oracle.normals_mt19937(1, 1.0, 1)
+    assert rel(gpu.mc_eur(*P1, 1, "call", replay=w).price, oracle.mc_eur(*P1, 1, "call", w)) < REPLAY_TOL or \
+        gpu.mc_eur(*P1, 1, "call", replay=w).price == oracle.mc_eur(*P1, 1, "call", w)
+    w = oracle.normals_mt19937(4, math.sqrt(1 / 5), 5)
+    assert abs(gpu.mc_amer(*P1, 2, 5, "put", replay=w).price - oracle.mc_amer(*P1, 2, 5, "put", w)) < 1e-10
+    w = oracle.normals_mt19937(4, 1.0, 3)
+    assert rel(gpu.mc_asia(*P1, 3, 1, "call", replay=w).price, oracle.mc_asia(*P1, 3, 1, "call", w)) < REPLAY_TOL or \
+        gpu.mc_asia(*P1, 3, 1, "call", replay=w).price == 0.0
+    # M = 1 American: no exercise dates before maturity
+    w = oracle.normals_mt19937(4, 1.0, 500)
+    assert rel(gpu.mc_amer(*P1, 1000, 1, "put", replay=w).price, oracle.mc_amer(*P1, 1000, 1, "put", w)) < REPLAY_TOL
+    # tiny lattices
+    for N in (1, 2, 3, 4, 15, 16, 17):
+        for pf in ("call", "put"):
+            g = gpu.binom(100, 95, .05, .3, 1, N, pf).price
+            o = oracle.binom(100, 95, .05, .3, 1, N, pf)
+            assert abs(g - o) < 1e-11 * max(1, abs(o)), (N, pf)
+
+
+def test_error_behaviour(gpu):
+    with pytest.raises(ValueError, match="divisible by 2"):
+        gpu.mc_amer(*P1, 1001, 10, "put")                      # reference include/common.h:180
+    with pytest.raises(ValueError, match="Unknown payoff"):
+        gpu.mc_asia(*P1, 100, 10, "digital")                   # reference src/mc_asia.cpp:56
+    with pytest.raises(ValueError):
+        gpu.mc_eur_multi(*P1, 100, "call", 33, 0.5)            # beyond PCF_MAX_ASSETS
+    with pytest.raises(ValueError, match="positive definite"):
+        gpu.mc_eur_multi(*P1, 100, "call", 4, -0.5)
+    with pytest.raises(ValueError):
+        gpu.mc_eur(*P1, 100, "call", replay=np.zeros(50))      # replay stream too short
+    with pytest.raises(ValueError):
+        gpu.mc_eur(*P1, 0, "call")
+    # all paths identical (sigma = 0) with S > E: x'x is singular -> the reference throws (common.h:115-117)
+    with pytest.raises(ValueError, match="Detereminant"):
+        gpu.mc_amer(100, 90, .05, 0.0, 1, 1000, 10, "call")
+
+
+def test_multi_gpu_in_process_matches_single(gpu):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    one = gpu.mc_asia(*P1, 1_000_001, 252, "call", seed=31)
+    am1 = gpu.mc_amer(*P1, 1_000_002, 50, "put", seed=31)
+    bn1 = gpu.binom(*P1, 1_000_001, "call")
+    gpu.shutdown()
+    gpu.init(2)
+    try:
+        two = gpu.mc_asia(*P1, 1_000_001, 252, "call", seed=31)
+        am2 = gpu.mc_amer(*P1, 1_000_002, 50, "put", seed=31)
+        bn2 = gpu.binom(*P1, 1_000_001, "call")
+        assert two.gpus == 2
+        assert rel(two.price, one.price) < 1e-13 and rel(am2.price, am1.price) < 1e-13
+        assert rel(bn2.price, bn1.price) < 1e-13
+    finally:
+        gpu.shutdown()
+        gpu.init(1)
