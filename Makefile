@@ -5,7 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off
 CSRC      := parcompfin_b200/csrc
 SRCS      := $(CSRC)/pcf_api.cu $(CSRC)/mc_kernels.cu $(CSRC)/amer_kernels.cu $(CSRC)/binom_kernels.cu $(CSRC)/peaks.cu
-OBJS      := $(SRCS:.cu=.o)
+OBJS      := $(SRCS:.cu=.o) $(CSRC)/fastmath_tables.o
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/pcf.h
 LIB       := parcompfin_b200/libpcf.so
 HOST      := parcompfin_b200/host
@@ -17,6 +17,8 @@ all: lib bins oracle
 lib: $(LIB)
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(@:.o=.ptxas.log) || { cat $(@:.o=.ptxas.log); exit 1; }
+$(CSRC)/fastmath_tables.o: $(CSRC)/fastmath_tables.cpp $(CSRC)/fastmath.cuh
+	$(HOSTCXX) -std=c++17 -O2 -fPIC -fvisibility=hidden -ffp-contract=off -c $< -o $@
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $(OBJS) -ldl -lpthread
 

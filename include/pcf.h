@@ -114,7 +114,7 @@ PCF_API int pcf_binom_embar(const pcf_params* p, pcf_result* out);
 /* --- diagnostics / test support ----------------------------------------------------------------- */
 /* The normal variates the native-mode kernels consume ("normal stream v1"):
  *   Philox4x32-10, key = seed, counter = (index lo, index hi, t/2, stream); X1 = x1:x0, X2 = x3:x2;
- *   u1 = 1 - (X1>>12)*2^-52, u2 = ((X2>>12)+1/2)*2^-52; z(index, t) = sqrt(-2 ln u1) *
+ *   u1 = 1 - (X1>>12)*2^-52, u2 = ((X2>>6)+1/2)*2^-58; z(index, t) = sqrt(-2 ln u1) *
  *   (t even ? cos : sin)(2 pi u2).  Writes out[i*T + t] = scale*z(index0+i, t) to HOST memory, so a
  *   native run can be replayed through the CPU oracle. Runs on the first context's GPU. */
 PCF_API int pcf_normal_stream(unsigned long long seed, unsigned int stream, unsigned long long index0,

@@ -351,9 +351,9 @@ ORACLE_API double oracle_binom(double S0, double E, double r, double sigma, doub
 // used to check the CUDA generator: Philox4x32-10 (Salmon et al., SC'11; Random123 KAT vectors in
 // tests/test_oracle.py) keyed by the 64-bit seed, counter = (index lo, index hi, draw/2, stream);
 // one call yields a Box-Muller pair:
-//   a = X1 >> 12, b = X2 >> 12 (X1 = x1:x0, X2 = x3:x2)
-//   u1 = 1 - a*2^-52 in (0,1],  u2 = (b + 1/2)*2^-52 in (0,1)
-//   (z_even, z_odd) = sqrt(-2 ln u1) * (cos 2 pi u2, sin 2 pi u2)
+//   X1 = x1:x0, X2 = x3:x2
+//   u1 = 1 - (X1 >> 12)*2^-52 in (0,1],  u2 = ((X2 >> 6) + 1/2)*2^-58 in (0,1)
+//   (z_even, z_odd) = sqrt(-2 ln u1) * (cos 2 pi u2, sin 2 pi u2), evaluated here in long double
 ORACLE_API void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
   for (int round = 0; round < 10; ++round) {
@@ -373,13 +373,13 @@ ORACLE_API void oracle_normal_pair(uint64_t seed, uint64_t index, uint32_t block
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t x[4];
   oracle_philox4x32_10(ctr, key, x);
-  uint64_t a = (((uint64_t)x[1] << 32) | x[0]) >> 12, b = (((uint64_t)x[3] << 32) | x[2]) >> 12;
-  double u1 = 1.0 - (double)a * 0x1p-52;
-  double u2 = ((double)b + 0.5) * 0x1p-52;
-  double R = std::sqrt(-2.0 * std::log(u1));
-  const double two_pi = 6.283185307179586476925286766559;
-  *z_even = R * std::cos(two_pi * u2);
-  *z_odd = R * std::sin(two_pi * u2);
+  const uint64_t X1 = ((uint64_t)x[1] << 32) | x[0], X2 = ((uint64_t)x[3] << 32) | x[2];
+  const double u1 = 1.0 - (double)(X1 >> 12) * 0x1p-52;                 // exact
+  const long double u2 = ((long double)(X2 >> 6) + 0.5L) * 0x1p-58L;      // exact in the x87 64-bit mantissa
+  const long double R = sqrtl(-2.0L * logl((long double)u1));
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  *z_even = (double)(R * cosl(two_pi * u2));
+  *z_odd = (double)(R * sinl(two_pi * u2));
 }
 
 // out[i*T + t] = scale * z(index0 + i, t), t < T  (the layout every replay stream above uses).

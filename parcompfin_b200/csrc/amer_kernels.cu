@@ -34,6 +34,7 @@ struct AmerArgs {
   double S0, E;
   double adt;   // (r - sigma^2/2) dt
   double cs;    // sigma*sd (native) | sigma (replay)
+  double exp_adt;  // e^{adt} (host, glibc)
   int cp, M;
   long long p0;       // first global pair of this GPU
   long long H;        // local pairs; Nl = 2H
@@ -42,30 +43,55 @@ struct AmerArgs {
 };
 
 // a6: one thread per antithetic pair, S+ and S- in registers, one Philox block per two dates.
-template <bool kReplay>
-__global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, double* __restrict__ paths,
+// exp((r-s^2/2)dt +- s w) = e^{a} e^{+-x}: with |x| small (kSmallExp) both factors come from one even/odd
+// Taylor split (13 FP64 for the pair); otherwise two table-driven exponentials.
+template <bool kSmallExp>
+__device__ __forceinline__ void amer_step(double& Sp, double& Sm, double z, const AmerArgs& a, double ea,
+                                          const TableView& tv) {
+  const double sw = a.cs * z;
+  if (kSmallExp) {
+    double ep, em;
+    exp_small_pm(sw, ep, em);
+    Sp *= ea * ep;  // common.h:202
+    Sm *= ea * em;  // common.h:203
+  } else {
+    Sp *= exp_table(a.adt + sw, tv);
+    Sm *= exp_table(a.adt - sw, tv);
+  }
+}
+
+template <bool kReplay, bool kSmallExp>
+__global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, const MathTables* __restrict__ tables,
+                                                                double* __restrict__ paths,
                                                                 int* __restrict__ when,
                                                                 double* __restrict__ cash) {
+  extern __shared__ __align__(16) unsigned char tab_smem[];
+  const TableView tv = stage_tables(tables, tab_smem);
   const PhiloxKey key(a.seed);
   const long long Nl = 2 * a.H;
+  const double ea = a.exp_adt;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.H;
        p += (long long)gridDim.x * blockDim.x) {
     double Sp = a.S0, Sm = a.S0;
-    double z0 = 0.0, z1 = 0.0;
-    for (int m = 1; m <= a.M; ++m) {
-      double z;
-      if (kReplay) {
-        z = a.w[p * (long long)a.M + (m - 1)];
-      } else {
-        if ((m - 1) % 2 == 0)
-          normal_pair(key, (uint64_t)(a.p0 + p), (uint32_t)((m - 1) >> 1), PCF_STREAM_AMER, z0, z1);
-        z = ((m - 1) % 2 == 0) ? z0 : z1;
+    if (kReplay) {
+      for (int m = 1; m <= a.M; ++m) {
+        amer_step<kSmallExp>(Sp, Sm, a.w[p * (long long)a.M + (m - 1)], a, ea, tv);
+        __stcs(paths + (size_t)(m - 1) * Nl + p, Sp);
+        __stcs(paths + (size_t)(m - 1) * Nl + p + a.H, Sm);
       }
-      double sw = a.cs * z;
-      Sp *= exp(a.adt + sw);  // common.h:202
-      Sm *= exp(a.adt - sw);  // common.h:203
-      __stcs(paths + (size_t)(m - 1) * Nl + p, Sp);
-      __stcs(paths + (size_t)(m - 1) * Nl + p + a.H, Sm);
+    } else {
+      for (int m = 1; m <= a.M; m += 2) {
+        double z0, z1;
+        normal_pair(key, (uint64_t)(a.p0 + p), (uint32_t)((m - 1) >> 1), PCF_STREAM_AMER, tv, z0, z1);
+        amer_step<kSmallExp>(Sp, Sm, z0, a, ea, tv);
+        __stcs(paths + (size_t)(m - 1) * Nl + p, Sp);
+        __stcs(paths + (size_t)(m - 1) * Nl + p + a.H, Sm);
+        if (m + 1 <= a.M) {
+          amer_step<kSmallExp>(Sp, Sm, z1, a, ea, tv);
+          __stcs(paths + (size_t)m * Nl + p, Sp);
+          __stcs(paths + (size_t)m * Nl + p + a.H, Sm);
+        }
+      }
     }
     // mc_amer.cpp:23-27: exercise_when = M, exercise_st = payoff(S_M)
     when[p] = a.M;
@@ -246,11 +272,15 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   a.cs = d_replay ? p.sigma : p.sigma * sqrt(dt);
   a.p0 = pairs.begin; a.H = H; a.seed = p.seed; a.w = d_replay;
 
-  int grid_gen = grid_for(c, H, kAmerBlock, 8);
+  a.exp_adt = exp(a.adt);
+  const bool small = fabs(a.cs) * kZMax <= kSmallExpBound;
+  int grid_gen = grid_for(c, H, kAmerBlock, 4);
   if (d_replay)
-    amer_paths_kernel<true><<<grid_gen, kAmerBlock, 0, c.stream>>>(a, paths, when, cash);
+    amer_paths_kernel<true, false><<<grid_gen, kAmerBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, paths, when, cash);
+  else if (small)
+    amer_paths_kernel<false, true><<<grid_gen, kAmerBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, paths, when, cash);
   else
-    amer_paths_kernel<false><<<grid_gen, kAmerBlock, 0, c.stream>>>(a, paths, when, cash);
+    amer_paths_kernel<false, false><<<grid_gen, kAmerBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, paths, when, cash);
   c.launches++;
   PCF_CUDA(cudaGetLastError());
 

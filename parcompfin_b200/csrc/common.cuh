@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <string>
 #include "../../include/pcf.h"
+#include "fastmath.cuh"
 
 namespace pcf {
 
@@ -41,6 +42,7 @@ struct Ctx {
   unsigned int* d_ticket = nullptr;
   double* d_out = nullptr;         // small result vector (64 doubles)
   int* d_flag = nullptr;           // device-side error flag
+  const MathTables* d_tables = nullptr;  // fastmath.cuh lookup tables (global memory; staged to smem per block)
   double* h_out = nullptr;         // pinned mirror of d_out
   void* workspace = nullptr;       // grow-only scratch (mc_amer path store, replay streams)
   size_t workspace_bytes = 0;

@@ -9,6 +9,7 @@
 namespace pcf {
 
 constexpr int kBlock = 256;
+constexpr int kBlocksPerSM = 4;  // resident CTAs per SM the grids are sized for (registers: <= 64/thread)
 
 // ------------------------------------------------------------------------------------------------
 // a1  reference src/mc_eur.cpp:23-26
@@ -21,10 +22,12 @@ struct EurArgs {
   const double* w;    // replay: w[n - 2*k0], already N(0,T)
 };
 
-template <bool kReplay>
-__global__ void __launch_bounds__(kBlock) mc_eur_kernel(EurArgs a, double* partials,
-                                                        unsigned int* ticket, double* out) {
+template <bool kReplay, bool kSmallExp>
+__global__ void __launch_bounds__(kBlock) mc_eur_kernel(EurArgs a, const MathTables* __restrict__ tables,
+                                                        double* partials, unsigned int* ticket, double* out) {
   __shared__ double smem[2 * 2 * 32];
+  extern __shared__ __align__(16) unsigned char tab_smem[];
+  const TableView tv = stage_tables(tables, tab_smem);
   const PhiloxKey key(a.seed);
   BlockedComp<4> s1, s2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -36,12 +39,12 @@ __global__ void __launch_bounds__(kBlock) mc_eur_kernel(EurArgs a, double* parti
       w1 = has2 ? a.w[2 * (k - a.k0) + 1] : 0.0;
     } else {
       double z0, z1;
-      normal_pair(key, (uint64_t)k, 0u, PCF_STREAM_EUR, z0, z1);
+      normal_pair(key, (uint64_t)k, 0u, PCF_STREAM_EUR, tv, z0, z1);
       w0 = a.sqrtT * z0;
       w1 = a.sqrtT * z1;
     }
-    double v0 = payoff(a.S0 * exp(fma(a.sigma, w0, a.drift)), a.E, a.cp);
-    double v1 = has2 ? payoff(a.S0 * exp(fma(a.sigma, w1, a.drift)), a.E, a.cp) : 0.0;
+    double v0 = payoff(a.S0 * exp_any<kSmallExp>(fma(a.sigma, w0, a.drift), tv), a.E, a.cp);
+    double v1 = has2 ? payoff(a.S0 * exp_any<kSmallExp>(fma(a.sigma, w1, a.drift), tv), a.E, a.cp) : 0.0;
     s1.add(v0 + v1);
     s2.add(fma(v0, v0, v1 * v1));
   }
@@ -56,11 +59,14 @@ int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay)
   a.sqrtT = sqrt(p.T);
   a.k0 = pairs.begin; a.k1 = pairs.end;
   a.seed = p.seed; a.w = d_replay;
-  int grid = grid_for(c, pairs.size(), kBlock, 8);
+  int grid = grid_for(c, pairs.size(), kBlock, kBlocksPerSM);
+  const bool small = fabs(a.drift) + fabs(a.sigma * a.sqrtT) * kZMax <= kSmallExpBound;
   if (d_replay)
-    mc_eur_kernel<true><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+    mc_eur_kernel<true, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+  else if (small)
+    mc_eur_kernel<false, true><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
   else
-    mc_eur_kernel<false><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+    mc_eur_kernel<false, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
@@ -81,15 +87,19 @@ struct AsiaArgs {
   const double* dB;  // replay: dB[(n-n0)*M + m]
 };
 
-__device__ __forceinline__ void asia_step(double& S, double& I, double z, const AsiaArgs& a) {
-  I = fma(S, fma(a.ch, z, a.c0), I);   // I += St*(1 + r dt/2 + sigma dB/2), pre-update St  (:33)
-  S *= exp(fma(a.cs, z, a.adt));       // St *= exp((r - sigma^2/2) dt + sigma dB)            (:34)
+template <bool kSmallExp>
+__device__ __forceinline__ void asia_step(double& S, double& I, double z, const AsiaArgs& a,
+                                          const TableView& tv) {
+  I = fma(S, fma(a.ch, z, a.c0), I);                     // I += St*(1 + r dt/2 + sigma dB/2), pre-update St (:33)
+  S *= exp_any<kSmallExp>(fma(a.cs, z, a.adt), tv);      // St *= exp((r - sigma^2/2) dt + sigma dB)          (:34)
 }
 
-template <bool kReplay>
-__global__ void __launch_bounds__(kBlock) mc_asia_kernel(AsiaArgs a, double* partials,
-                                                         unsigned int* ticket, double* out) {
+template <bool kReplay, bool kSmallExp>
+__global__ void __launch_bounds__(kBlock) mc_asia_kernel(AsiaArgs a, const MathTables* __restrict__ tables,
+                                                         double* partials, unsigned int* ticket, double* out) {
   __shared__ double smem[2 * 2 * 32];
+  extern __shared__ __align__(16) unsigned char tab_smem[];
+  const TableView tv = stage_tables(tables, tab_smem);
   const PhiloxKey key(a.seed);
   Comp s1, s2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -98,19 +108,19 @@ __global__ void __launch_bounds__(kBlock) mc_asia_kernel(AsiaArgs a, double* par
     double S = a.S0, I = 0.0;
     if (kReplay) {
       const double* z = a.dB + (n - a.n0) * (long long)a.M;
-      for (int m = 0; m < a.M; ++m) asia_step(S, I, z[m], a);
+      for (int m = 0; m < a.M; ++m) asia_step<kSmallExp>(S, I, z[m], a, tv);
     } else {
       int m = 0;
       for (; m + 1 < a.M; m += 2) {
         double z0, z1;
-        normal_pair(key, (uint64_t)n, (uint32_t)(m >> 1), PCF_STREAM_ASIA, z0, z1);
-        asia_step(S, I, z0, a);
-        asia_step(S, I, z1, a);
+        normal_pair(key, (uint64_t)n, (uint32_t)(m >> 1), PCF_STREAM_ASIA, tv, z0, z1);
+        asia_step<kSmallExp>(S, I, z0, a, tv);
+        asia_step<kSmallExp>(S, I, z1, a, tv);
       }
       if (m < a.M) {
         double z0, z1;
-        normal_pair(key, (uint64_t)n, (uint32_t)(m >> 1), PCF_STREAM_ASIA, z0, z1);
-        asia_step(S, I, z0, a);
+        normal_pair(key, (uint64_t)n, (uint32_t)(m >> 1), PCF_STREAM_ASIA, tv, z0, z1);
+        asia_step<kSmallExp>(S, I, z0, a, tv);
       }
     }
     double v = payoff(I / Md, a.E, a.cp);  // :36
@@ -133,11 +143,14 @@ int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay
   a.invM = 1.0 / (double)p.M;
   a.n0 = paths.begin; a.n1 = paths.end;
   a.seed = p.seed; a.dB = d_replay;
-  int grid = grid_for(c, paths.size(), kBlock, 8);
+  int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
+  const bool small = fabs(a.adt) + fabs(a.cs) * kZMax <= kSmallExpBound;
   if (d_replay)
-    mc_asia_kernel<true><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+    mc_asia_kernel<true, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+  else if (small)
+    mc_asia_kernel<false, true><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
   else
-    mc_asia_kernel<false><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+    mc_asia_kernel<false, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
@@ -159,9 +172,11 @@ struct BasketArgs {
 };
 
 template <int D, bool kReplay>
-__global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, double* partials,
-                                                           unsigned int* ticket, double* out) {
+__global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const MathTables* __restrict__ tables,
+                                                           double* partials, unsigned int* ticket, double* out) {
   __shared__ double smem[2 * 2 * 32];
+  extern __shared__ __align__(16) unsigned char tab_smem[];
+  const TableView tv = stage_tables(tables, tab_smem);
   const PhiloxKey key(a.seed);
   Comp s1, s2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -179,7 +194,7 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, double*
           z0 = z[2 * j];
           z1 = (2 * j + 1 < a.d) ? z[2 * j + 1] : 0.0;
         } else {
-          normal_pair(key, (uint64_t)n, (uint32_t)j, PCF_STREAM_BASKET, z0, z1);
+          normal_pair(key, (uint64_t)n, (uint32_t)j, PCF_STREAM_BASKET, tv, z0, z1);
         }
 #pragma unroll
         for (int i = 2 * j; i < D; ++i) bt[i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j], z0, bt[i]);
@@ -193,7 +208,7 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, double*
     double basket = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i)
-      if (i < a.d) basket = fma(a.wS0, exp(fma(a.sigma, bt[i], a.drift)), basket);  // :30
+      if (i < a.d) basket = fma(a.wS0, exp_table(fma(a.sigma, bt[i], a.drift), tv), basket);  // :30
     double v = payoff(basket, a.E, a.cp);
     s1.add(v);
     s2.add(v * v);
@@ -205,9 +220,9 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, double*
 template <int D>
 static void launch_basket(Ctx& c, const BasketArgs& a, int grid, bool replay) {
   if (replay)
-    mc_basket_kernel<D, true><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+    mc_basket_kernel<D, true><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
   else
-    mc_basket_kernel<D, false><<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+    mc_basket_kernel<D, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
 }
 
 int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-major */,
@@ -223,7 +238,7 @@ int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-m
   a.wS0 = (1.0 / (double)d) * p.S0;
   a.n0 = paths.begin; a.n1 = paths.end;
   a.seed = p.seed; a.Z = d_replay;
-  int grid = grid_for(c, paths.size(), kBlock, 4);
+  int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
   const bool rp = d_replay != nullptr;
   if (d <= 2) launch_basket<2>(c, a, grid, rp);
   else if (d <= 4) launch_basket<4>(c, a, grid, rp);
@@ -246,7 +261,9 @@ __global__ void philox_kat_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 }
 
 __global__ void normal_stream_kernel(uint64_t seed, uint32_t stream, uint64_t index0, long long count,
-                                     int T, double scale, double* out) {
+                                     int T, double scale, const MathTables* __restrict__ tables, double* out) {
+  extern __shared__ __align__(16) unsigned char tab_smem[];
+  const TableView tv = stage_tables(tables, tab_smem);
   const PhiloxKey key(seed);
   const int blocks = (T + 1) / 2;
   const long long total = count * blocks;
@@ -255,7 +272,7 @@ __global__ void normal_stream_kernel(uint64_t seed, uint32_t stream, uint64_t in
     long long i = g / blocks;
     int j = (int)(g - i * blocks);
     double z0, z1;
-    normal_pair(key, index0 + (uint64_t)i, (uint32_t)j, stream, z0, z1);
+    normal_pair(key, index0 + (uint64_t)i, (uint32_t)j, stream, tv, z0, z1);
     out[i * (long long)T + 2 * j] = scale * z0;
     if (2 * j + 1 < T) out[i * (long long)T + 2 * j + 1] = scale * z1;
   }
@@ -272,7 +289,7 @@ int run_normal_stream(Ctx& c, uint64_t seed, uint32_t stream, uint64_t index0, l
                       double scale, double* d_out) {
   long long total = count * ((T + 1) / 2);
   int grid = grid_for(c, total, kBlock, 8);
-  normal_stream_kernel<<<grid, kBlock, 0, c.stream>>>(seed, stream, index0, count, T, scale, d_out);
+  normal_stream_kernel<<<grid, kBlock, kTableSmemBytes, c.stream>>>(seed, stream, index0, count, T, scale, c.d_tables, d_out);
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
 }

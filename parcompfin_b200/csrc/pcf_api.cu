@@ -34,6 +34,7 @@ int run_normal_stream(Ctx& c, uint64_t seed, uint32_t stream, uint64_t index0, l
                       double scale, double* d_out);
 int run_fp64_peak(Ctx& c, double seconds_target, double* dfma_per_sec);
 int run_hbm_peak(Ctx& c, long long bytes, double* bytes_per_sec);
+void build_math_tables(MathTables& t);
 
 // ---- error text --------------------------------------------------------------------------------
 static std::mutex g_err_mu;
@@ -118,6 +119,13 @@ static int ctx_open(Ctx& c, int device, int rank, int world) {
   PCF_CUDA(cudaMemset(c.d_out, 0, sizeof(double) * 64));
   PCF_CUDA(cudaMemset(c.d_flag, 0, sizeof(int)));
   PCF_CUDA(cudaMallocHost(&c.h_out, sizeof(double) * 64));
+  static MathTables host_tables;
+  static std::once_flag once;
+  std::call_once(once, [] { build_math_tables(host_tables); });
+  MathTables* dt = nullptr;
+  PCF_CUDA(cudaMalloc(&dt, sizeof(MathTables)));
+  PCF_CUDA(cudaMemcpy(dt, &host_tables, sizeof(MathTables), cudaMemcpyHostToDevice));
+  c.d_tables = dt;
   return PCF_OK;
 }
 
@@ -126,6 +134,7 @@ static void ctx_close(Ctx& c) {
   if (c.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.comm);
   if (c.workspace) cudaFree(c.workspace);
   if (c.h_out) cudaFreeHost(c.h_out);
+  if (c.d_tables) cudaFree((void*)c.d_tables);
   if (c.d_flag) cudaFree(c.d_flag);
   if (c.d_out) cudaFree(c.d_out);
   if (c.d_ticket) cudaFree(c.d_ticket);

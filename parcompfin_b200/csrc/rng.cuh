@@ -6,6 +6,7 @@
 // so 1/2/4/8 GPUs consume identical variates.
 #pragma once
 #include <cstdint>
+#include "fastmath.cuh"
 
 namespace pcf {
 
@@ -48,27 +49,59 @@ __device__ __forceinline__ void philox4x32_10(const PhiloxKey& key, uint32_t c0,
   out[3] = c3;
 }
 
-// Box-Muller pair from one Philox block.
-//   a = X1 >> 12, b = X2 >> 12;  u1 = 1 - a*2^-52 in (0,1];  2*u2 = (2b+1)*2^-52 in (0,2)
-//   (z_even, z_odd) = sqrt(-2 ln u1) * (cos, sin)(pi * 2 u2)
-// The two uniforms are built by bit injection into [1,2) + one exact FP64 op each (no I2F).
-__device__ __forceinline__ void box_muller_pair(const uint32_t x[4], double& z_even, double& z_odd) {
-  double d1 = __hiloint2double((int)(0x3FF00000u | (x[1] >> 12)), (int)((x[1] << 20) | (x[0] >> 12)));
-  double d2 = __hiloint2double((int)(0x3FF00000u | (x[3] >> 12)), (int)((x[3] << 20) | (x[2] >> 12)));
-  double u1 = 2.0 - d1;                                // exact
-  double t2 = fma(d2, 2.0, -2.0 + 0x1p-52);            // exact: (2b+1)*2^-52
-  double R = sqrt(-2.0 * log(u1));
-  double s, c;
-  sincospi(t2, &s, &c);
+// Box-Muller pair from one Philox block ("normal stream v1", include/pcf.h):
+//   X1 = x1:x0, X2 = x3:x2;  a = X1 >> 12;  u1 = 1 - a 2^-52 in (0,1];  u2 = ((X2 >> 6) + 1/2) 2^-58 in (0,1)
+//   (z_even, z_odd) = sqrt(-2 ln u1) * (cos, sin)(2 pi u2)
+// u1 is built by bit injection into [1,2) and one exact subtraction (no I2F); the angle never exists as
+// a double: its top 6 bits pick a sector, the other 52 fill a mantissa (fastmath.cuh).
+// 33 FP64-pipe instructions per pair (CUDA math library: 67).
+__device__ __forceinline__ void box_muller_pair(const uint32_t x[4], const TableView& tv, double& z_even,
+                                                double& z_odd) {
+  const double d1 = __hiloint2double((int)(0x3FF00000u | (x[1] >> 12)), (int)((x[1] << 20) | (x[0] >> 12)));
+  const double u1 = 2.0 - d1;  // exact
+  const double R = sqrt_pos(neg2log_unit(u1, tv));
+  double c, s;
+  sincos_2pi_bits(x[2], x[3], tv, c, s);
   z_even = R * c;
   z_odd = R * s;
 }
 
 __device__ __forceinline__ void normal_pair(const PhiloxKey& key, uint64_t index, uint32_t block,
-                                            uint32_t stream, double& z_even, double& z_odd) {
+                                            uint32_t stream, const TableView& tv, double& z_even,
+                                            double& z_odd) {
   uint32_t x[4];
   philox4x32_10(key, (uint32_t)index, (uint32_t)(index >> 32), block, stream, x);
-  box_muller_pair(x, z_even, z_odd);
+  box_muller_pair(x, tv, z_even, z_odd);
+}
+
+// Stages the lookup tables of fastmath.cuh from global memory into this block's dynamic shared memory,
+// replicated per bank group, and returns the calling thread's view. Ends with __syncthreads().
+__device__ __forceinline__ TableView stage_tables(const MathTables* __restrict__ g, unsigned char* smem) {
+  Pair* ln_s = reinterpret_cast<Pair*>(smem);
+  Pair* sc_s = ln_s + kLnEntries * kRep16;
+  double* ex_s = reinterpret_cast<double*>(sc_s + kScEntries * kRep16);
+  for (int i = threadIdx.x; i < kLnEntries * kRep16; i += blockDim.x) ln_s[i] = g->ln_tab[i / kRep16];
+  for (int i = threadIdx.x; i < kScEntries * kRep16; i += blockDim.x) sc_s[i] = g->sc_tab[i / kRep16];
+  for (int i = threadIdx.x; i < kExpEntries * kRep8; i += blockDim.x) ex_s[i] = g->exp_tab[i / kRep8];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  TableView tv;
+  tv.ln_tab = ln_s + (lane & (kRep16 - 1));
+  tv.sc_tab = sc_s + (lane & (kRep16 - 1));
+  tv.exp_tab = ex_s + (lane & (kRep8 - 1));
+  tv.stride16 = kRep16;
+  tv.stride8 = kRep8;
+  return tv;
+}
+
+// |x| bound under which exp_small() may replace exp_table(): |x| <= |a| + |b| * kZMax with
+// kZMax = sqrt(2 * 52 ln 2), the largest |z| the stream can produce (u1 >= 2^-52).
+constexpr double kZMax = 8.5;
+constexpr double kSmallExpBound = 0.11;
+
+template <bool kSmall>
+__device__ __forceinline__ double exp_any(double x, const TableView& tv) {
+  return kSmall ? exp_small(x) : exp_table(x, tv);
 }
 
 }  // namespace pcf

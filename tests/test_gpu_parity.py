@@ -180,7 +180,12 @@ def test_binom_matches_published_csv(gpu, golden):
     for c in golden["reference_vectors"]["binom_embar_csv"]:
         S0, E, r, sigma, T = c["params"]
         g = gpu.binom(S0, E, r, sigma, T, c["N"], c["payoff"])
-        assert rel(g.price, c["price"]) < 2e-9, c  # printed with 10 significant digits
+        # printed with 10 significant digits; beyond 32000 steps the published value itself is off the exact
+        # sum of its lattice by up to 5.5e-9 (N = 80000: published 26.61220685, exact 26.6122069974621652,
+        # mpmath) because comb() accumulates rounding error
+        assert rel(g.price, c["price"]) < (2e-9 if c["N"] <= 32000 else 1e-8), c
+    g = gpu.binom(100, 110, 0.02, 0.75, 1, 80000, "call")
+    assert rel(g.price, 26.612206997462165204) < 1e-12
 
 
 def test_binom_matches_exact_sum(gpu, golden):
