@@ -47,11 +47,11 @@ struct AmerArgs {
 // Taylor split (13 FP64 for the pair); otherwise two table-driven exponentials.
 template <bool kSmallExp>
 __device__ __forceinline__ void amer_step(double& Sp, double& Sm, double z, const AmerArgs& a, double ea,
-                                          const TableView& tv) {
+                                          const TableView& tv, const Hoisted& hc) {
   const double sw = a.cs * z;
   if (kSmallExp) {
     double ep, em;
-    exp_small_pm(sw, ep, em);
+    exp_small_pm(sw, hc, ep, em);
     Sp *= ea * ep;  // common.h:202
     Sm *= ea * em;  // common.h:203
   } else {
@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, cons
                                                                 double* __restrict__ cash) {
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
+  Hoisted hc;
+  hc.load();
   const PhiloxKey key(a.seed);
   const long long Nl = 2 * a.H;
   const double ea = a.exp_adt;
@@ -75,19 +77,19 @@ __global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, cons
     double Sp = a.S0, Sm = a.S0;
     if (kReplay) {
       for (int m = 1; m <= a.M; ++m) {
-        amer_step<kSmallExp>(Sp, Sm, a.w[p * (long long)a.M + (m - 1)], a, ea, tv);
+        amer_step<kSmallExp>(Sp, Sm, a.w[p * (long long)a.M + (m - 1)], a, ea, tv, hc);
         __stcs(paths + (size_t)(m - 1) * Nl + p, Sp);
         __stcs(paths + (size_t)(m - 1) * Nl + p + a.H, Sm);
       }
     } else {
       for (int m = 1; m <= a.M; m += 2) {
         double z0, z1;
-        normal_pair(key, (uint64_t)(a.p0 + p), (uint32_t)((m - 1) >> 1), PCF_STREAM_AMER, tv, z0, z1);
-        amer_step<kSmallExp>(Sp, Sm, z0, a, ea, tv);
+        normal_pair(key, (uint64_t)(a.p0 + p), (uint32_t)((m - 1) >> 1), PCF_STREAM_AMER, tv, hc, z0, z1);
+        amer_step<kSmallExp>(Sp, Sm, z0, a, ea, tv, hc);
         __stcs(paths + (size_t)(m - 1) * Nl + p, Sp);
         __stcs(paths + (size_t)(m - 1) * Nl + p + a.H, Sm);
         if (m + 1 <= a.M) {
-          amer_step<kSmallExp>(Sp, Sm, z1, a, ea, tv);
+          amer_step<kSmallExp>(Sp, Sm, z1, a, ea, tv, hc);
           __stcs(paths + (size_t)m * Nl + p, Sp);
           __stcs(paths + (size_t)m * Nl + p + a.H, Sm);
         }
@@ -104,6 +106,29 @@ __global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, cons
 // a7 pass 1 (mc_amer.cpp:41-59): moments over in-the-money paths at date m.
 // out[0..7] = n_itm, Sx, Sx^2, Sx^3, Sx^4, Sy, Syx, Syx^2. Products are formed exactly like the
 // reference forms them (left to right, no FMA) so that only the summation order differs.
+// HBM-bound: each thread streams two paths per iteration (16 B vector loads of S, state loads only for
+// in-the-money lanes); the eight sums run as plain FP64 adds over kMomFold iterations and are then folded
+// into compensated totals, so the compensation costs ~1 add per path instead of 7.
+constexpr int kMomFold = 8;
+
+__device__ __forceinline__ void amer_moment_terms(double S, int wq, double cs, double E, int cp, int m,
+                                                  const double* s_disc, double (&run)[8]) {
+  if (payoff(S, E, cp) > 0.0) {
+    const double ex = __dadd_rn(S, -E);
+    const double cont = __dmul_rn(s_disc[(wq & ~kQuirkBit) - m], cs);
+    const double ex2 = __dmul_rn(ex, ex), ex3 = __dmul_rn(ex2, ex), ex4 = __dmul_rn(ex3, ex);
+    const double yx = __dmul_rn(cont, ex), yx2 = __dmul_rn(yx, ex);
+    run[0] += 1.0;
+    run[1] += ex;
+    run[2] += ex2;
+    run[3] += ex3;
+    run[4] += ex4;
+    run[5] += cont;
+    run[6] += yx;
+    run[7] += yx2;
+  }
+}
+
 __global__ void __launch_bounds__(kAmerBlock) amer_moments_kernel(
     const double* __restrict__ S_row, const int* __restrict__ when, const double* __restrict__ cash,
     long long Nl, double E, int cp, int m, int M, double* partials, unsigned int* ticket, double* out) {
@@ -111,31 +136,37 @@ __global__ void __launch_bounds__(kAmerBlock) amer_moments_kernel(
   extern __shared__ double s_disc[];  // lanes index it with different k: shared memory, not constant
   for (int k = threadIdx.x; k <= M; k += blockDim.x) s_disc[k] = c_disc_fwd[k];
   __syncthreads();
-  BlockedComp<8> acc[8];
-  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < Nl;
-       n += (long long)gridDim.x * blockDim.x) {
-    double S = __ldcs(S_row + n);
-    double pv = payoff(S, E, cp);
-    if (pv > 0.0) {
-      double ex = __dadd_rn(S, -E);
-      int k = (when[n] & ~kQuirkBit) - m;
-      double cont = __dmul_rn(s_disc[k], cash[n]);
-      double ex2 = __dmul_rn(ex, ex), ex3 = __dmul_rn(ex2, ex), ex4 = __dmul_rn(ex3, ex);
-      double yx = __dmul_rn(cont, ex), yx2 = __dmul_rn(yx, ex);
-      acc[0].add(1.0);
-      acc[1].add(ex);
-      acc[2].add(ex2);
-      acc[3].add(ex3);
-      acc[4].add(ex4);
-      acc[5].add(cont);
-      acc[6].add(yx);
-      acc[7].add(yx2);
+  Comp acc[8];
+  double run[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int fold = 0;
+  const long long pairs = Nl >> 1;  // Nl is even
+  const double2* S2 = reinterpret_cast<const double2*>(S_row);
+  const int2* W2 = reinterpret_cast<const int2*>(when);
+  const double2* C2 = reinterpret_cast<const double2*>(cash);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double2 S = __ldcs(S2 + i);
+    const bool itm0 = payoff(S.x, E, cp) > 0.0, itm1 = payoff(S.y, E, cp) > 0.0;
+    int2 w = make_int2(0, 0);
+    double2 c = make_double2(0.0, 0.0);
+    if (itm0 || itm1) {
+      w = W2[i];
+      c = C2[i];
+    }
+    amer_moment_terms(S.x, w.x, c.x, E, cp, m, s_disc, run);
+    amer_moment_terms(S.y, w.y, c.y, E, cp, m, s_disc, run);
+    if (++fold == kMomFold) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[k].add(run[k]);
+        run[k] = 0.0;
+      }
+      fold = 0;
     }
   }
-  Comp v[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = acc[i].finish();
-  grid_reduce<8>(v, smem, partials, ticket, out);
+  for (int k = 0; k < 8; ++k) acc[k].add(run[k]);
+  grid_reduce<8>(acc, smem, partials, ticket, out);
 }
 
 // a8: include/common.h:98-141 in the reference's operation order (cyclic %3 indexing, adjugate /
@@ -192,27 +223,34 @@ __global__ void __launch_bounds__(kAmerBlock) amer_decide_kernel(
   const int mode = s_mode;
   if (mode == 0) return;
   const double c0 = s_coef[0], c1 = s_coef[1], c2 = s_coef[2];
-  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < Nl;
-       n += (long long)gridDim.x * blockDim.x) {
-    double S = __ldcs(S_row + n);
-    double pv = payoff(S, E, cp);
-    if (!(pv > 0.0)) continue;
-    if (mode == 2) {
-      double x = __dadd_rn(S, -E);
-      if (x == -1.0) continue;  // the reference's sentinel collision (mc_amer.cpp:32,98)
-      double yhat = __dadd_rn(__dadd_rn(c0, __dmul_rn(c1, x)), __dmul_rn(c2, __dmul_rn(x, x)));
-      double pq = payoff(x, E, cp);  // payoff of the SHIFTED value (mc_amer.cpp:100)
-      if (pq > yhat) {
-        when[n] = m | kQuirkBit;
-        cash[n] = pv;
-      }
-    } else {
-      // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against discounted cash flow
-      int k = (when[n] & ~kQuirkBit) - m;
-      double cont = __dmul_rn(c_disc_fwd[k], cash[n]);
-      if (pv > cont) {
-        when[n] = m;
-        cash[n] = pv;
+  const long long pairs = Nl >> 1;
+  const double2* S2 = reinterpret_cast<const double2*>(S_row);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double2 S2v = __ldcs(S2 + i);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double S = h ? S2v.y : S2v.x;
+      const long long n = 2 * i + h;
+      const double pv = payoff(S, E, cp);
+      if (!(pv > 0.0)) continue;
+      if (mode == 2) {
+        const double x = __dadd_rn(S, -E);
+        if (x == -1.0) continue;  // the reference's sentinel collision (mc_amer.cpp:32,98)
+        const double yhat = __dadd_rn(__dadd_rn(c0, __dmul_rn(c1, x)), __dmul_rn(c2, __dmul_rn(x, x)));
+        const double pq = payoff(x, E, cp);  // payoff of the SHIFTED value (mc_amer.cpp:100)
+        if (pq > yhat) {
+          when[n] = m | kQuirkBit;
+          cash[n] = pv;
+        }
+      } else {
+        // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against discounted cash flow
+        const int k = (when[n] & ~kQuirkBit) - m;
+        const double cont = __dmul_rn(c_disc_fwd[k], cash[n]);
+        if (pv > cont) {
+          when[n] = m;
+          cash[n] = pv;
+        }
       }
     }
   }

@@ -82,6 +82,20 @@ static const double h_coef[kCoefCount] = PCF_COEF_VALUES;
 #define K(i) h_coef[i]
 #endif
 
+// A DFMA takes at most one constant-bank operand, so the first Horner step of every polynomial
+// (two coefficients) needs one of them in a vector register. Loading these once per thread, before the hot
+// loop, keeps LDC (and its scoreboard wait) out of the loop body.
+struct Hoisted {
+  double ln1, s5, c6, e8, e7;
+  PCF_HD void load() {
+    ln1 = K(kLn1);
+    s5 = K(kS5);
+    c6 = K(kC6);
+    e8 = K(kE8);
+    e7 = K(kE7);
+  }
+};
+
 PCF_HD double make_double(uint32_t hi, uint32_t lo) {
 #ifdef __CUDA_ARCH__
   return __hiloint2double((int)hi, (int)lo);
@@ -116,14 +130,14 @@ PCF_HD uint32_t lo_word(double d) {
 // bin j = bits 19..13 of the re-based high word, r = m * rc_j - 1 (one FMA, |r| <= 2^-8),
 //   -2 ln u = e (-2 ln 2) + 2 ln rc_j - 2 log1p(r),  -2 log1p(r) = r(-2 + r(1 + r(-2/3 + r(1/2 + r(-2/5 + r/3)))))
 // The table's 2^-56 bias keeps the result strictly positive at u = 1 (its absolute error is ~1e-16 anyway).
-PCF_HD double neg2log_unit(double u, const TableView& tv) {
+PCF_HD double neg2log_unit(double u, const TableView& tv, const Hoisted& hc) {
   const uint32_t hx = hi_word(u) + 0x00095F62u;                 // 0x3FF00000 - 0x3FE6A09E
   const uint32_t idx = (hx >> 13) & 0x7Fu;
   const Pair e = tv.ln_tab[idx * tv.stride16];
   const double m = make_double((hx & 0x000FFFFFu) + 0x3FE6A09Eu, lo_word(u));
   const double ed = make_double(0x43300000u, hx >> 20) - K(kLnEMagic);  // (2^52 + biased) - (2^52 + 1023)
   const double r = fma(m, e.x, K(kNegOne));
-  double q = fma(r, K(kLn0), K(kLn1));   // 1/3, -2/5
+  double q = fma(r, K(kLn0), hc.ln1);    // 1/3, -2/5
   q = fma(q, r, K(kLn2));                // 1/2
   q = fma(q, r, K(kLn3));                // -2/3
   q = fma(q, r, K(kLn4));                // 1
@@ -153,17 +167,18 @@ PCF_HD double sqrt_pos(double t) {
 // sector = top 6 bits of X2 (table of cos/sin at the sector centre); the next 52 bits f fill a mantissa,
 // w = 1 + f 2^-52, and the offset from the centre is x = (pi/32)(w - 3/2 + 2^-53), |x| < pi/64:
 // sin to x^7, cos to x^8, then one rotation.
-PCF_HD void sincos_2pi_bits(uint32_t x2, uint32_t x3, const TableView& tv, double& c_out, double& s_out) {
+PCF_HD void sincos_2pi_bits(uint32_t x2, uint32_t x3, const TableView& tv, const Hoisted& hc, double& c_out,
+                            double& s_out) {
   const uint32_t sector = x3 >> 26;
   const Pair cs = tv.sc_tab[sector * tv.stride16];
   const double w = make_double(0x3FF00000u | ((x3 >> 6) & 0x000FFFFFu), (x3 << 26) | (x2 >> 6));
   const double x = fma(w, K(kScA), K(kScB));  // pi/32, -(pi/32)(3/2 - 2^-53)
   const double x2d = x * x;
-  double ps = fma(x2d, K(kS7), K(kS5));
+  double ps = fma(x2d, K(kS7), hc.s5);
   ps = fma(ps, x2d, K(kS3));
   const double x3d = x * x2d;
   const double s = fma(x3d, ps, x);
-  double pc = fma(x2d, K(kC8), K(kC6));
+  double pc = fma(x2d, K(kC8), hc.c6);
   pc = fma(pc, x2d, K(kC4));
   pc = fma(pc, x2d, K(kC2));
   const double c = fma(pc, x2d, K(kOne));
@@ -172,8 +187,8 @@ PCF_HD void sincos_2pi_bits(uint32_t x2, uint32_t x3, const TableView& tv, doubl
 }
 
 // ---- e^x for |x| <= 0.11 (per-step GBM increments): Taylor degree 9, truncation < 2.6e-17 relative ------
-PCF_HD double exp_small(double x) {
-  double p = fma(x, K(kE9), K(kE8));
+PCF_HD double exp_small(double x, const Hoisted& hc) {
+  double p = fma(x, K(kE9), hc.e8);
   p = fma(p, x, K(kE7));
   p = fma(p, x, K(kE6));
   p = fma(p, x, K(kE5));
@@ -206,14 +221,14 @@ PCF_HD double exp_table(double x, const TableView& tv) {
 }
 
 // e^(a+x) and e^(a-x) for |x| <= 0.11 from one even/odd split (antithetic pairs): 13 FP64 for both.
-PCF_HD void exp_small_pm(double x, double& ep, double& em) {
+PCF_HD void exp_small_pm(double x, const Hoisted& hc, double& ep, double& em) {
   const double x2 = x * x;
-  double ce = fma(x2, K(kE10), K(kE8));
+  double ce = fma(x2, K(kE10), hc.e8);
   ce = fma(ce, x2, K(kE6));
   ce = fma(ce, x2, K(kE4));
   ce = fma(ce, x2, K(kE2));
   ce = fma(ce, x2, K(kOne));
-  double so = fma(x2, K(kE9), K(kE7));
+  double so = fma(x2, K(kE9), hc.e7);
   so = fma(so, x2, K(kE5));
   so = fma(so, x2, K(kE3));
   so = fma(so, x2, K(kOne));

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "reduce.cuh"
 #include "rng.cuh"
+#include <cstdlib>
 
 namespace pcf {
 
@@ -28,6 +29,8 @@ __global__ void __launch_bounds__(kBlock) mc_eur_kernel(EurArgs a, const MathTab
   __shared__ double smem[2 * 2 * 32];
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
+  Hoisted hc;
+  hc.load();
   const PhiloxKey key(a.seed);
   BlockedComp<4> s1, s2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -39,12 +42,12 @@ __global__ void __launch_bounds__(kBlock) mc_eur_kernel(EurArgs a, const MathTab
       w1 = has2 ? a.w[2 * (k - a.k0) + 1] : 0.0;
     } else {
       double z0, z1;
-      normal_pair(key, (uint64_t)k, 0u, PCF_STREAM_EUR, tv, z0, z1);
+      normal_pair(key, (uint64_t)k, 0u, PCF_STREAM_EUR, tv, hc, z0, z1);
       w0 = a.sqrtT * z0;
       w1 = a.sqrtT * z1;
     }
-    double v0 = payoff(a.S0 * exp_any<kSmallExp>(fma(a.sigma, w0, a.drift), tv), a.E, a.cp);
-    double v1 = has2 ? payoff(a.S0 * exp_any<kSmallExp>(fma(a.sigma, w1, a.drift), tv), a.E, a.cp) : 0.0;
+    double v0 = payoff(a.S0 * exp_any<kSmallExp>(fma(a.sigma, w0, a.drift), tv, hc), a.E, a.cp);
+    double v1 = has2 ? payoff(a.S0 * exp_any<kSmallExp>(fma(a.sigma, w1, a.drift), tv, hc), a.E, a.cp) : 0.0;
     s1.add(v0 + v1);
     s2.add(fma(v0, v0, v1 * v1));
   }
@@ -88,47 +91,104 @@ struct AsiaArgs {
 };
 
 template <bool kSmallExp>
-__device__ __forceinline__ void asia_step(double& S, double& I, double z, const AsiaArgs& a,
-                                          const TableView& tv) {
-  I = fma(S, fma(a.ch, z, a.c0), I);                     // I += St*(1 + r dt/2 + sigma dB/2), pre-update St (:33)
-  S *= exp_any<kSmallExp>(fma(a.cs, z, a.adt), tv);      // St *= exp((r - sigma^2/2) dt + sigma dB)          (:34)
+__device__ __forceinline__ void asia_step(double& S, double& I, double z, double ch, double c0, double cs,
+                                          double adt, const TableView& tv, const Hoisted& hc) {
+  I = fma(S, fma(ch, z, c0), I);                        // I += St*(1 + r dt/2 + sigma dB/2), pre-update St (:33)
+  S *= exp_any<kSmallExp>(fma(cs, z, adt), tv, hc);     // St *= exp((r - sigma^2/2) dt + sigma dB)          (:34)
 }
 
-template <bool kReplay, bool kSmallExp>
-__global__ void __launch_bounds__(kBlock) mc_asia_kernel(AsiaArgs a, const MathTables* __restrict__ tables,
-                                                         double* partials, unsigned int* ticket, double* out) {
+// Replay flavour: normals come from HBM in the reference's draw order (parity path, not the fast path).
+__global__ void __launch_bounds__(kBlock) mc_asia_replay_kernel(AsiaArgs a, const MathTables* __restrict__ tables,
+                                                                double* partials, unsigned int* ticket,
+                                                                double* out) {
   __shared__ double smem[2 * 2 * 32];
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
-  const PhiloxKey key(a.seed);
+  Hoisted hc;
+  hc.load();
   Comp s1, s2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const double Md = (double)a.M;
   for (long long n = a.n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < a.n1; n += stride) {
     double S = a.S0, I = 0.0;
-    if (kReplay) {
-      const double* z = a.dB + (n - a.n0) * (long long)a.M;
-      for (int m = 0; m < a.M; ++m) asia_step<kSmallExp>(S, I, z[m], a, tv);
-    } else {
-      int m = 0;
-      for (; m + 1 < a.M; m += 2) {
-        double z0, z1;
-        normal_pair(key, (uint64_t)n, (uint32_t)(m >> 1), PCF_STREAM_ASIA, tv, z0, z1);
-        asia_step<kSmallExp>(S, I, z0, a, tv);
-        asia_step<kSmallExp>(S, I, z1, a, tv);
-      }
-      if (m < a.M) {
-        double z0, z1;
-        normal_pair(key, (uint64_t)n, (uint32_t)(m >> 1), PCF_STREAM_ASIA, tv, z0, z1);
-        asia_step<kSmallExp>(S, I, z0, a, tv);
-      }
-    }
+    const double* z = a.dB + (n - a.n0) * (long long)a.M;
+    for (int m = 0; m < a.M; ++m) asia_step<false>(S, I, z[m], a.ch, a.c0, a.cs, a.adt, tv, hc);
     double v = payoff(I / Md, a.E, a.cp);  // :36
     s1.add(v);
     s2.add(v * v);
   }
   Comp v[2] = {s1, s2};
   grid_reduce<2>(v, smem, partials, ticket, out);
+}
+
+// Native flavour. kPaths independent paths per thread are advanced in lock step: their Philox rounds and
+// FP64 chains are independent instruction streams in one loop body, which gives every warp integer AND
+// FP64 work to issue at any time (ILP instead of relying on 8+ resident warps being out of phase).
+template <bool kSmallExp, int kPaths, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
+mc_asia_kernel(AsiaArgs a, const MathTables* __restrict__ tables, double* partials, unsigned int* ticket,
+               double* out) {
+  __shared__ double smem[2 * 2 * 32];
+  extern __shared__ __align__(16) unsigned char tab_smem[];
+  const TableView tv = stage_tables(tables, tab_smem);
+  Hoisted hc;
+  hc.load();
+  const PhiloxKey key(a.seed);
+  Comp s1, s2;
+  const long long T = (long long)gridDim.x * blockDim.x;
+  const double Md = (double)a.M;
+  const double ch = a.ch, c0 = a.c0, cs = a.cs, adt = a.adt;
+  for (long long base = a.n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; base < a.n1; base += T * kPaths) {
+    double S[kPaths], I[kPaths];
+    uint32_t lo[kPaths], hi[kPaths];
+#pragma unroll
+    for (int p = 0; p < kPaths; ++p) {
+      const long long n = base + p * T;  // may run past n1 in the last sweep: computed, not accumulated
+      S[p] = a.S0;
+      I[p] = 0.0;
+      lo[p] = (uint32_t)n;
+      hi[p] = (uint32_t)((uint64_t)n >> 32);
+    }
+    int m = 0;
+    for (; m + 1 < a.M; m += 2) {
+#pragma unroll
+      for (int p = 0; p < kPaths; ++p) {
+        uint32_t x[4];
+        philox4x32_10(key, lo[p], hi[p], (uint32_t)(m >> 1), PCF_STREAM_ASIA, x);
+        double z0, z1;
+        box_muller_pair(x, tv, hc, z0, z1);
+        asia_step<kSmallExp>(S[p], I[p], z0, ch, c0, cs, adt, tv, hc);
+        asia_step<kSmallExp>(S[p], I[p], z1, ch, c0, cs, adt, tv, hc);
+      }
+    }
+    if (m < a.M) {
+#pragma unroll
+      for (int p = 0; p < kPaths; ++p) {
+        uint32_t x[4];
+        philox4x32_10(key, lo[p], hi[p], (uint32_t)(m >> 1), PCF_STREAM_ASIA, x);
+        double z0, z1;
+        box_muller_pair(x, tv, hc, z0, z1);
+        asia_step<kSmallExp>(S[p], I[p], z0, ch, c0, cs, adt, tv, hc);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kPaths; ++p) {
+      if (base + p * T < a.n1) {
+        double v = payoff(I[p] / Md, a.E, a.cp);  // :36
+        s1.add(v);
+        s2.add(v * v);
+      }
+    }
+  }
+  Comp v[2] = {s1, s2};
+  grid_reduce<2>(v, smem, partials, ticket, out);
+}
+
+template <bool kSmallExp, int kPaths, int kMinBlocks>
+static void launch_asia(Ctx& c, const AsiaArgs& a, long long paths) {
+  int grid = grid_for(c, (paths + kPaths - 1) / kPaths, kBlock, kMinBlocks);
+  mc_asia_kernel<kSmallExp, kPaths, kMinBlocks><<<grid, kBlock, kTableSmemBytes, c.stream>>>(
+      a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
 }
 
 int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay) {
@@ -143,14 +203,39 @@ int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay
   a.invM = 1.0 / (double)p.M;
   a.n0 = paths.begin; a.n1 = paths.end;
   a.seed = p.seed; a.dB = d_replay;
-  int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
   const bool small = fabs(a.adt) + fabs(a.cs) * kZMax <= kSmallExpBound;
-  if (d_replay)
-    mc_asia_kernel<true, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
-  else if (small)
-    mc_asia_kernel<false, true><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
-  else
-    mc_asia_kernel<false, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+  if (d_replay) {
+    int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
+    mc_asia_replay_kernel<<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+  } else {
+    // launch shape: PCF_ASIA_VARIANT = <paths per thread><min blocks per SM>, e.g. "14", "23" (tuning knob)
+    const char* v = getenv("PCF_ASIA_VARIANT");
+    const int variant = v ? atoi(v) : 41;
+#define PCF_ASIA_CASE(P, B)                                   \
+  case P * 10 + B:                                            \
+    if (small) launch_asia<true, P, B>(c, a, paths.size());   \
+    else launch_asia<false, P, B>(c, a, paths.size());        \
+    break;
+    switch (variant) {
+      PCF_ASIA_CASE(1, 3)
+      PCF_ASIA_CASE(1, 4)
+      PCF_ASIA_CASE(1, 5)
+      PCF_ASIA_CASE(1, 6)
+      PCF_ASIA_CASE(2, 2)
+      PCF_ASIA_CASE(2, 3)
+      PCF_ASIA_CASE(2, 4)
+      PCF_ASIA_CASE(3, 2)
+      PCF_ASIA_CASE(3, 1)
+      PCF_ASIA_CASE(4, 1)
+      PCF_ASIA_CASE(4, 2)
+      PCF_ASIA_CASE(6, 1)
+      PCF_ASIA_CASE(8, 1)
+      default:
+        set_last_error("unknown PCF_ASIA_VARIANT");
+        return PCF_EINVAL;
+    }
+#undef PCF_ASIA_CASE
+  }
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
@@ -177,6 +262,8 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const M
   __shared__ double smem[2 * 2 * 32];
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
+  Hoisted hc;
+  hc.load();
   const PhiloxKey key(a.seed);
   Comp s1, s2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -194,7 +281,7 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const M
           z0 = z[2 * j];
           z1 = (2 * j + 1 < a.d) ? z[2 * j + 1] : 0.0;
         } else {
-          normal_pair(key, (uint64_t)n, (uint32_t)j, PCF_STREAM_BASKET, tv, z0, z1);
+          normal_pair(key, (uint64_t)n, (uint32_t)j, PCF_STREAM_BASKET, tv, hc, z0, z1);
         }
 #pragma unroll
         for (int i = 2 * j; i < D; ++i) bt[i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j], z0, bt[i]);
@@ -264,6 +351,8 @@ __global__ void normal_stream_kernel(uint64_t seed, uint32_t stream, uint64_t in
                                      int T, double scale, const MathTables* __restrict__ tables, double* out) {
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
+  Hoisted hc;
+  hc.load();
   const PhiloxKey key(seed);
   const int blocks = (T + 1) / 2;
   const long long total = count * blocks;
@@ -272,7 +361,7 @@ __global__ void normal_stream_kernel(uint64_t seed, uint32_t stream, uint64_t in
     long long i = g / blocks;
     int j = (int)(g - i * blocks);
     double z0, z1;
-    normal_pair(key, index0 + (uint64_t)i, (uint32_t)j, stream, tv, z0, z1);
+    normal_pair(key, index0 + (uint64_t)i, (uint32_t)j, stream, tv, hc, z0, z1);
     out[i * (long long)T + 2 * j] = scale * z0;
     if (2 * j + 1 < T) out[i * (long long)T + 2 * j + 1] = scale * z1;
   }

@@ -55,23 +55,23 @@ __device__ __forceinline__ void philox4x32_10(const PhiloxKey& key, uint32_t c0,
 // u1 is built by bit injection into [1,2) and one exact subtraction (no I2F); the angle never exists as
 // a double: its top 6 bits pick a sector, the other 52 fill a mantissa (fastmath.cuh).
 // 33 FP64-pipe instructions per pair (CUDA math library: 67).
-__device__ __forceinline__ void box_muller_pair(const uint32_t x[4], const TableView& tv, double& z_even,
-                                                double& z_odd) {
+__device__ __forceinline__ void box_muller_pair(const uint32_t x[4], const TableView& tv, const Hoisted& hc,
+                                                double& z_even, double& z_odd) {
   const double d1 = __hiloint2double((int)(0x3FF00000u | (x[1] >> 12)), (int)((x[1] << 20) | (x[0] >> 12)));
   const double u1 = 2.0 - d1;  // exact
-  const double R = sqrt_pos(neg2log_unit(u1, tv));
+  const double R = sqrt_pos(neg2log_unit(u1, tv, hc));
   double c, s;
-  sincos_2pi_bits(x[2], x[3], tv, c, s);
+  sincos_2pi_bits(x[2], x[3], tv, hc, c, s);
   z_even = R * c;
   z_odd = R * s;
 }
 
 __device__ __forceinline__ void normal_pair(const PhiloxKey& key, uint64_t index, uint32_t block,
-                                            uint32_t stream, const TableView& tv, double& z_even,
-                                            double& z_odd) {
+                                            uint32_t stream, const TableView& tv, const Hoisted& hc,
+                                            double& z_even, double& z_odd) {
   uint32_t x[4];
   philox4x32_10(key, (uint32_t)index, (uint32_t)(index >> 32), block, stream, x);
-  box_muller_pair(x, tv, z_even, z_odd);
+  box_muller_pair(x, tv, hc, z_even, z_odd);
 }
 
 // Stages the lookup tables of fastmath.cuh from global memory into this block's dynamic shared memory,
@@ -100,8 +100,8 @@ constexpr double kZMax = 8.5;
 constexpr double kSmallExpBound = 0.11;
 
 template <bool kSmall>
-__device__ __forceinline__ double exp_any(double x, const TableView& tv) {
-  return kSmall ? exp_small(x) : exp_table(x, tv);
+__device__ __forceinline__ double exp_any(double x, const TableView& tv, const Hoisted& hc) {
+  return kSmall ? exp_small(x, hc) : exp_table(x, tv);
 }
 
 }  // namespace pcf

@@ -13,6 +13,8 @@ int main() {
   static MathTables T;
   build_math_tables(T);
   TableView tv{T.ln_tab, T.sc_tab, T.exp_tab, 1, 1};
+  Hoisted hc;
+  hc.load();
   std::mt19937_64 g(12345);
   const int n = 2000000;
   // -2 ln u on the stream's own grid u = 1 - a 2^-52, incl. the ends
@@ -23,7 +25,7 @@ int main() {
     else if (i < 64) a = (1ull << 52) - 1 - (uint64_t)(i - 32); // u = 2^-52, ...
     else if (i & 1) a >>= (g() % 50);                           // many magnitudes of 1 - u
     double u = 1.0 - (double)a * 0x1p-52;
-    double got = neg2log_unit(u, tv);
+    double got = neg2log_unit(u, tv, hc);
     long double want = -2.0L * logl((long double)u);
     double err = (double)fabsl((long double)got - want);
     if (err > e_abs) e_abs = err;
@@ -48,7 +50,7 @@ int main() {
     if (i < 64) X2 = ((uint64_t)i << 58);
     else if (i < 128) X2 = ((uint64_t)(i - 64) << 58) | ((1ull << 58) - 1);
     double c, s;
-    sincos_2pi_bits((uint32_t)X2, (uint32_t)(X2 >> 32), tv, c, s);
+    sincos_2pi_bits((uint32_t)X2, (uint32_t)(X2 >> 32), tv, hc, c, s);
     long double u2 = ((long double)(X2 >> 6) + 0.5L) * 0x1p-58L;
     double ec = (double)fabsl((long double)c - cosl(two_pi * u2)), es = (double)fabsl((long double)s - sinl(two_pi * u2));
     if (ec > e_sc) e_sc = ec;
@@ -61,12 +63,12 @@ int main() {
   double e_es = 0, e_et = 0, e_pm = 0;
   for (int i = 0; i < n; ++i) {
     double x = ((double)(g() >> 11) * 0x1p-53 - 0.5) * 0.22;
-    double got = exp_small(x);
+    double got = exp_small(x, hc);
     long double want = expl((long double)x);
     double err = (double)fabsl((long double)got - want) / ulp_of((double)want);
     if (err > e_es) e_es = err;
     double ep, em;
-    exp_small_pm(x, ep, em);
+    exp_small_pm(x, hc, ep, em);
     err = (double)fabsl((long double)ep - want) / ulp_of((double)want);
     if (err > e_pm) e_pm = err;
     err = (double)fabsl((long double)em - expl(-(long double)x)) / ulp_of((double)expl(-(long double)x));
