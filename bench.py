@@ -296,6 +296,9 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["config"], "paths": args.paths or w["N"], "dates": w["M"],
                        "parallelism": f"paths sharded by global index over {n_gpus} GPU(s)",
+                       "collective": ("none (1 GPU)" if n_gpus == 1 else
+                                      "NVLink peer-memory mailbox: P2P stores issued by the reducing kernel (csrc/xchg.cuh)"
+                                      if pcf.peer_active() else "ncclAllReduce on the compute stream"),
                        "l2": "no input arrays: the kernel reads no global memory (parameters only), nothing to flush; "
                              "the mc_amer entry in `others` streams a 40 GB path store (>> 126 MB L2)",
                        "price": m["price"], "std_error": m["se"]},

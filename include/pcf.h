@@ -95,6 +95,15 @@ PCF_API int pcf_init(int gpus);
  * (src/mc_eur_mpi.cpp:58-66). */
 PCF_API int pcf_init_rank(int rank, int world, int device, const unsigned char* nccl_id);
 PCF_API int pcf_nccl_unique_id(unsigned char id[128]);
+/* NVLink peer-memory exchange between processes (one per GPU, same node): every rank exports the CUDA IPC handle
+ * of its 1 KB mailbox after pcf_init_rank(), the caller all-gathers the world x 64 bytes by any transport and
+ * hands them to pcf_ipc_import(). From then on partial moments travel as P2P stores issued by the reducing
+ * kernel itself (csrc/xchg.cuh) instead of ncclAllReduce. pcf_init(G) sets this up by itself.
+ * pcf_peer_enable(0) switches back to NCCL (requires a communicator); pcf_peer_active() reports the mode. */
+PCF_API int pcf_ipc_export(unsigned char handle[64]);
+PCF_API int pcf_ipc_import(const unsigned char* handles, int world);
+PCF_API int pcf_peer_enable(int on);
+PCF_API int pcf_peer_active(void);
 PCF_API int pcf_shutdown(void);
 PCF_API int pcf_world_size(void);
 

@@ -28,6 +28,7 @@ MAX_ASSETS = 32
 # every symbol include/pcf.h declares (tests check the library exports all of them)
 EXPORTS = (
     "pcf_init", "pcf_init_rank", "pcf_nccl_unique_id", "pcf_shutdown", "pcf_world_size",
+    "pcf_ipc_export", "pcf_ipc_import", "pcf_peer_enable", "pcf_peer_active",
     "pcf_mc_eur", "pcf_mc_eur_multi", "pcf_mc_asia", "pcf_mc_amer", "pcf_binom_embar",
     "pcf_normal_stream", "pcf_philox4x32_10", "pcf_chol_equicorr", "pcf_fp64_peak", "pcf_hbm_peak",
     "pcf_device_info", "pcf_strerror", "pcf_last_error",
@@ -96,6 +97,10 @@ def load_library() -> ctypes.CDLL:
     lib.pcf_init_rank.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
     lib.pcf_init_rank.restype = ctypes.c_int
     lib.pcf_nccl_unique_id.argtypes, lib.pcf_nccl_unique_id.restype = [ctypes.c_char_p], ctypes.c_int
+    lib.pcf_ipc_export.argtypes, lib.pcf_ipc_export.restype = [ctypes.c_char_p], ctypes.c_int
+    lib.pcf_ipc_import.argtypes, lib.pcf_ipc_import.restype = [ctypes.c_char_p, ctypes.c_int], ctypes.c_int
+    lib.pcf_peer_enable.argtypes, lib.pcf_peer_enable.restype = [ctypes.c_int], ctypes.c_int
+    lib.pcf_peer_active.argtypes, lib.pcf_peer_active.restype = [], ctypes.c_int
     lib.pcf_shutdown.argtypes, lib.pcf_shutdown.restype = [], ctypes.c_int
     lib.pcf_world_size.argtypes, lib.pcf_world_size.restype = [], ctypes.c_int
     lib.pcf_normal_stream.argtypes = [ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_ulonglong,
@@ -146,6 +151,27 @@ def nccl_unique_id() -> bytes:
 def init_rank(rank: int, world: int, device: int, nccl_id: bytes | None = None) -> None:
     """One process per GPU; ``nccl_id`` is rank 0's :func:`nccl_unique_id`, distributed by the caller."""
     _check(load_library().pcf_init_rank(rank, world, device, nccl_id))
+
+
+def ipc_export() -> bytes:
+    """CUDA IPC handle (64 bytes) of this rank's exchange mailbox."""
+    buf = ctypes.create_string_buffer(64)
+    _check(load_library().pcf_ipc_export(buf))
+    return buf.raw
+
+
+def ipc_import(handles: list[bytes]) -> None:
+    """Maps every rank's mailbox (handles in rank order) for the NVLink peer-memory exchange."""
+    blob = b"".join(handles)
+    _check(load_library().pcf_ipc_import(blob, len(handles)))
+
+
+def peer_enable(on: bool) -> None:
+    _check(load_library().pcf_peer_enable(1 if on else 0))
+
+
+def peer_active() -> bool:
+    return bool(load_library().pcf_peer_active())
 
 
 def shutdown() -> None:

@@ -131,7 +131,8 @@ __device__ __forceinline__ void amer_moment_terms(double S, int wq, double cs, d
 
 __global__ void __launch_bounds__(kAmerBlock) amer_moments_kernel(
     const double* __restrict__ S_row, const int* __restrict__ when, const double* __restrict__ cash,
-    long long Nl, double E, int cp, int m, int M, double* partials, unsigned int* ticket, double* out) {
+    long long Nl, double E, int cp, int m, int M, PeerLink link, double* partials, unsigned int* ticket,
+    double* out) {
   __shared__ double smem[8 * 2 * 32];
   extern __shared__ double s_disc[];  // lanes index it with different k: shared memory, not constant
   for (int k = threadIdx.x; k <= M; k += blockDim.x) s_disc[k] = c_disc_fwd[k];
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(kAmerBlock) amer_moments_kernel(
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k].add(run[k]);
-  grid_reduce<8>(acc, smem, partials, ticket, out);
+  grid_reduce<8>(acc, smem, partials, ticket, out, &link);
 }
 
 // a8: include/common.h:98-141 in the reference's operation order (cyclic %3 indexing, adjugate /
@@ -199,9 +200,19 @@ __device__ bool solve3_reference_order(const double* mom, double coef[3]) {
 // a7 pass 2 (mc_amer.cpp:73-106): exercise decision at date m from the (all-reduced) moments.
 __global__ void __launch_bounds__(kAmerBlock) amer_decide_kernel(
     const double* __restrict__ S_row, int* __restrict__ when, double* __restrict__ cash, long long Nl,
-    double E, int cp, int m, const double* __restrict__ mom, int* err_flag) {
+    double E, int cp, int m, const double* __restrict__ mom_local, PeerLink link, int* err_flag) {
   __shared__ double s_coef[3];
+  __shared__ double s_mom[kXchgVals];
   __shared__ int s_mode;  // 0 skip, 1 few-paths branch, 2 regression branch
+  // Multi-GPU: the moments of every rank arrive in this GPU's mailbox (published by the last block of each rank's
+  // moments kernel); wait for them here instead of running a collective between the two passes.
+  if (link.world > 1) {
+    peer_gather<kXchgVals>(link, s_mom);
+  } else {
+    if (threadIdx.x < kXchgVals) s_mom[threadIdx.x] = mom_local[threadIdx.x];
+    __syncthreads();
+  }
+  const double* mom = s_mom;
   if (threadIdx.x == 0) {
     double cnt = mom[0];
     if (cnt == 0.0) {
@@ -260,8 +271,8 @@ __global__ void __launch_bounds__(kAmerBlock) amer_decide_kernel(
 __global__ void __launch_bounds__(kAmerBlock) amer_final_kernel(const int* __restrict__ when,
                                                                 const double* __restrict__ cash,
                                                                 long long Nl, double E, int cp, int M,
-                                                                double* partials, unsigned int* ticket,
-                                                                double* out) {
+                                                                PeerLink link, double* partials,
+                                                                unsigned int* ticket, double* out) {
   __shared__ double smem[2 * 2 * 32];
   extern __shared__ double s_disc[];
   for (int k = threadIdx.x; k <= M; k += blockDim.x) s_disc[k] = c_disc_abs[k];
@@ -277,12 +288,13 @@ __global__ void __launch_bounds__(kAmerBlock) amer_final_kernel(const int* __res
     s2.add(v * v);
   }
   Comp v[2] = {s1.finish(), s2.finish()};
-  grid_reduce<2>(v, smem, partials, ticket, out);
+  grid_reduce<2>(v, smem, partials, ticket, out, &link);
 }
 
 // Host driver for one GPU. Enqueues everything on c.stream; result (sum, sumsq of discounted cash
 // flows over local paths) lands in c.d_out[0..1]; c.d_out[8..15] is the per-date moment vector.
-int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset) {
+int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset,
+                PeerLink* final_link) {
   const int M = p.M;
   if (M > kMaxDates) {
     set_last_error("mc_amer: M exceeds kMaxDates");
@@ -326,13 +338,17 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   double* mom = c.d_out + 8;
   for (int m = M - 1; m > 0; --m) {
     const double* row = paths + (size_t)(m - 1) * Nl;
+    // peer path: the moments kernel publishes into every GPU's mailbox and the decision kernel waits on it;
+    // NCCL path (no peer mapping): an all-reduce of the 8 doubles between the two kernels.
+    const PeerLink l = next_link(c);
     amer_moments_kernel<<<grid, kAmerBlock, sizeof(double) * (M + 1), c.stream>>>(
-        row, when, cash, Nl, p.E, p.cp, m, M, c.d_partials, c.d_ticket, mom);
-    PCF_TRY(allreduce_sum(c, mom, 8));
-    amer_decide_kernel<<<grid, kAmerBlock, 0, c.stream>>>(row, when, cash, Nl, p.E, p.cp, m, mom, c.d_flag);
+        row, when, cash, Nl, p.E, p.cp, m, M, l, c.d_partials, c.d_ticket, mom);
+    if (!use_peer(c)) PCF_TRY(allreduce_sum(c, mom, 8));
+    amer_decide_kernel<<<grid, kAmerBlock, 0, c.stream>>>(row, when, cash, Nl, p.E, p.cp, m, mom, l, c.d_flag);
     c.launches += 2;
   }
-  amer_final_kernel<<<grid, kAmerBlock, sizeof(double) * (M + 1), c.stream>>>(when, cash, Nl, p.E, p.cp, M,
+  *final_link = next_link(c);
+  amer_final_kernel<<<grid, kAmerBlock, sizeof(double) * (M + 1), c.stream>>>(when, cash, Nl, p.E, p.cp, M, *final_link,
                                                                                c.d_partials, c.d_ticket, c.d_out);
   c.launches++;
   PCF_CUDA(cudaGetLastError());

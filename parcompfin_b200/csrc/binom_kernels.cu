@@ -103,7 +103,7 @@ __device__ __forceinline__ double pair_terms(long long i, const BinomArgs& a) {
   return term(lw1, x, nx, a) + term(lw2, nx, x, a);
 }
 
-__global__ void __launch_bounds__(kBinomBlock) binom_terms_kernel(BinomArgs a, double* partials,
+__global__ void __launch_bounds__(kBinomBlock) binom_terms_kernel(BinomArgs a, PeerLink link, double* partials,
                                                                   unsigned int* ticket, double* out) {
   __shared__ double smem[1 * 2 * 32];
   Comp acc;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kBinomBlock) binom_terms_kernel(BinomArgs a, d
     acc.add(term(lpmf_inner(h, h, sh, sh, lf, a), h, h, a));
   }
   Comp v[1] = {acc};
-  grid_reduce<1>(v, smem, partials, ticket, out);
+  grid_reduce<1>(v, smem, partials, ticket, out, &link);
 }
 
 static long double stirlerr_host(long double n) {
@@ -145,7 +145,7 @@ void binom_lattice(double r, double sigma, double T, long long N, double& u, dou
 }
 
 // `pairs` = this GPU's slice of i in [lo, until); result (partial undiscounted sum) -> c.d_out[0].
-int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid) {
+int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid, const PeerLink& link) {
   BinomArgs a;
   double u, d, pp, q;
   binom_lattice(p.r, p.sigma, p.T, p.N, u, d, pp, q);
@@ -165,7 +165,7 @@ int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid) {
   }
   for (int k = 0; k < 16; ++k) a.sfe[k] = (double)stirlerr_host((long double)k);
   int grid = grid_for(c, pairs.size(), kBinomBlock, 8);
-  binom_terms_kernel<<<grid, kBinomBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_out);
+  binom_terms_kernel<<<grid, kBinomBlock, 0, c.stream>>>(a, link, c.d_partials, c.d_ticket, c.d_out);
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;

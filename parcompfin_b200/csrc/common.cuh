@@ -6,6 +6,7 @@
 #include <string>
 #include "../../include/pcf.h"
 #include "fastmath.cuh"
+#include "xchg.cuh"
 
 namespace pcf {
 
@@ -47,7 +48,28 @@ struct Ctx {
   void* workspace = nullptr;       // grow-only scratch (mc_amer path store, replay streams)
   size_t workspace_bytes = 0;
   int launches = 0;                // kernels launched in the current call
+  // NVLink peer-memory exchange (xchg.cuh). peer_ok: every rank's mailbox is mapped here; otherwise the job
+  // falls back to ncclAllReduce on the compute stream.
+  Mailbox* mailbox = nullptr;
+  PeerLink link{};
+  bool peer_ok = false;
+  unsigned long long xchg_seq = 0;
 };
+
+// Link for the next exchange of this call sequence (every rank issues the same sequence of exchanges).
+// Without peer mapping the returned link has world == 1, which turns publishing and gathering off.
+inline PeerLink next_link(Ctx& c) {
+  PeerLink l = c.link;
+  if (c.world > 1 && c.peer_ok) {
+    l.seq = ++c.xchg_seq;
+  } else {
+    l.world = 1;
+    l.seq = 0;
+  }
+  return l;
+}
+inline bool use_peer(const Ctx& c) { return c.world > 1 && c.peer_ok; }
+int launch_xchg_finish(Ctx& c, const PeerLink& l, int k, double* d_out);  // d_out[0..k) = sum over ranks
 
 int ctx_reserve(Ctx& c, size_t bytes);  // ensures c.workspace >= bytes
 int allreduce_sum(Ctx& c, double* d_buf, int count);  // in place, on c.stream; no-op if world == 1

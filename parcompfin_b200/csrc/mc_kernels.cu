@@ -24,7 +24,7 @@ struct EurArgs {
 };
 
 template <bool kReplay, bool kSmallExp>
-__global__ void __launch_bounds__(kBlock) mc_eur_kernel(EurArgs a, const MathTables* __restrict__ tables,
+__global__ void __launch_bounds__(kBlock) mc_eur_kernel(EurArgs a, const MathTables* __restrict__ tables, PeerLink link,
                                                         double* partials, unsigned int* ticket, double* out) {
   __shared__ double smem[2 * 2 * 32];
   extern __shared__ __align__(16) unsigned char tab_smem[];
@@ -52,10 +52,10 @@ __global__ void __launch_bounds__(kBlock) mc_eur_kernel(EurArgs a, const MathTab
     s2.add(fma(v0, v0, v1 * v1));
   }
   Comp v[2] = {s1.finish(), s2.finish()};
-  grid_reduce<2>(v, smem, partials, ticket, out);
+  grid_reduce<2>(v, smem, partials, ticket, out, &link);
 }
 
-int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay) {
+int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, const PeerLink& link) {
   EurArgs a;
   a.S0 = p.S0; a.E = p.E; a.sigma = p.sigma; a.cp = p.cp; a.N = p.N;
   a.drift = (p.r - p.sigma * p.sigma / 2) * p.T;
@@ -65,11 +65,11 @@ int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay)
   int grid = grid_for(c, pairs.size(), kBlock, kBlocksPerSM);
   const bool small = fabs(a.drift) + fabs(a.sigma * a.sqrtT) * kZMax <= kSmallExpBound;
   if (d_replay)
-    mc_eur_kernel<true, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+    mc_eur_kernel<true, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
   else if (small)
-    mc_eur_kernel<false, true><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+    mc_eur_kernel<false, true><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
   else
-    mc_eur_kernel<false, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+    mc_eur_kernel<false, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
@@ -99,8 +99,8 @@ __device__ __forceinline__ void asia_step(double& S, double& I, double z, double
 
 // Replay flavour: normals come from HBM in the reference's draw order (parity path, not the fast path).
 __global__ void __launch_bounds__(kBlock) mc_asia_replay_kernel(AsiaArgs a, const MathTables* __restrict__ tables,
-                                                                double* partials, unsigned int* ticket,
-                                                                double* out) {
+                                                                PeerLink link, double* partials,
+                                                                unsigned int* ticket, double* out) {
   __shared__ double smem[2 * 2 * 32];
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kBlock) mc_asia_replay_kernel(AsiaArgs a, cons
     s2.add(v * v);
   }
   Comp v[2] = {s1, s2};
-  grid_reduce<2>(v, smem, partials, ticket, out);
+  grid_reduce<2>(v, smem, partials, ticket, out, &link);
 }
 
 // Native flavour. kPaths independent paths per thread are advanced in lock step: their Philox rounds and
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(kBlock) mc_asia_replay_kernel(AsiaArgs a, cons
 // FP64 work to issue at any time (ILP instead of relying on 8+ resident warps being out of phase).
 template <bool kSmallExp, int kPaths, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
-mc_asia_kernel(AsiaArgs a, const MathTables* __restrict__ tables, double* partials, unsigned int* ticket,
-               double* out) {
+mc_asia_kernel(AsiaArgs a, const MathTables* __restrict__ tables, PeerLink link, double* partials,
+               unsigned int* ticket, double* out) {
   __shared__ double smem[2 * 2 * 32];
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
@@ -181,17 +181,17 @@ mc_asia_kernel(AsiaArgs a, const MathTables* __restrict__ tables, double* partia
     }
   }
   Comp v[2] = {s1, s2};
-  grid_reduce<2>(v, smem, partials, ticket, out);
+  grid_reduce<2>(v, smem, partials, ticket, out, &link);
 }
 
 template <bool kSmallExp, int kPaths, int kMinBlocks>
-static void launch_asia(Ctx& c, const AsiaArgs& a, long long paths) {
+static void launch_asia(Ctx& c, const AsiaArgs& a, long long paths, const PeerLink& link) {
   int grid = grid_for(c, (paths + kPaths - 1) / kPaths, kBlock, kMinBlocks);
   mc_asia_kernel<kSmallExp, kPaths, kMinBlocks><<<grid, kBlock, kTableSmemBytes, c.stream>>>(
-      a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+      a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
 }
 
-int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay) {
+int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay, const PeerLink& link) {
   AsiaArgs a;
   const double dt = (double)p.T / (double)p.M;
   const double sd = sqrt(dt);
@@ -206,15 +206,15 @@ int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay
   const bool small = fabs(a.adt) + fabs(a.cs) * kZMax <= kSmallExpBound;
   if (d_replay) {
     int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
-    mc_asia_replay_kernel<<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+    mc_asia_replay_kernel<<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
   } else {
     // launch shape: PCF_ASIA_VARIANT = <paths per thread><min blocks per SM>, e.g. "14", "23" (tuning knob)
     const char* v = getenv("PCF_ASIA_VARIANT");
     const int variant = v ? atoi(v) : 41;
 #define PCF_ASIA_CASE(P, B)                                   \
   case P * 10 + B:                                            \
-    if (small) launch_asia<true, P, B>(c, a, paths.size());   \
-    else launch_asia<false, P, B>(c, a, paths.size());        \
+    if (small) launch_asia<true, P, B>(c, a, paths.size(), link);   \
+    else launch_asia<false, P, B>(c, a, paths.size(), link);        \
     break;
     switch (variant) {
       PCF_ASIA_CASE(1, 3)
@@ -258,7 +258,8 @@ struct BasketArgs {
 
 template <int D, bool kReplay>
 __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const MathTables* __restrict__ tables,
-                                                           double* partials, unsigned int* ticket, double* out) {
+                                                           PeerLink link, double* partials, unsigned int* ticket,
+                                                           double* out) {
   __shared__ double smem[2 * 2 * 32];
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
@@ -301,19 +302,19 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const M
     s2.add(v * v);
   }
   Comp v[2] = {s1, s2};
-  grid_reduce<2>(v, smem, partials, ticket, out);
+  grid_reduce<2>(v, smem, partials, ticket, out, &link);
 }
 
 template <int D>
-static void launch_basket(Ctx& c, const BasketArgs& a, int grid, bool replay) {
+static void launch_basket(Ctx& c, const BasketArgs& a, int grid, bool replay, const PeerLink& link) {
   if (replay)
-    mc_basket_kernel<D, true><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+    mc_basket_kernel<D, true><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
   else
-    mc_basket_kernel<D, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, c.d_partials, c.d_ticket, c.d_out);
+    mc_basket_kernel<D, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
 }
 
 int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-major */,
-                  Shard paths, const double* d_replay) {
+                  Shard paths, const double* d_replay, const PeerLink& link) {
   const int d = p.assets;
   double Lpad[PCF_MAX_ASSETS * PCF_MAX_ASSETS] = {0};
   for (int i = 0; i < d; ++i)
@@ -327,11 +328,26 @@ int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-m
   a.seed = p.seed; a.Z = d_replay;
   int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
   const bool rp = d_replay != nullptr;
-  if (d <= 2) launch_basket<2>(c, a, grid, rp);
-  else if (d <= 4) launch_basket<4>(c, a, grid, rp);
-  else if (d <= 8) launch_basket<8>(c, a, grid, rp);
-  else if (d <= 16) launch_basket<16>(c, a, grid, rp);
-  else launch_basket<32>(c, a, grid, rp);
+  if (d <= 2) launch_basket<2>(c, a, grid, rp, link);
+  else if (d <= 4) launch_basket<4>(c, a, grid, rp, link);
+  else if (d <= 8) launch_basket<8>(c, a, grid, rp, link);
+  else if (d <= 16) launch_basket<16>(c, a, grid, rp, link);
+  else launch_basket<32>(c, a, grid, rp, link);
+  c.launches++;
+  PCF_CUDA(cudaGetLastError());
+  return PCF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-warp finisher of a peer-memory exchange: waits for every rank's flag, adds in rank order.
+__global__ void xchg_finish_kernel(PeerLink link, int k, double* out) {
+  __shared__ double s[kXchgVals];
+  peer_gather<kXchgVals>(link, s);
+  if ((int)threadIdx.x < k) out[threadIdx.x] = s[threadIdx.x];
+}
+
+int launch_xchg_finish(Ctx& c, const PeerLink& l, int k, double* d_out) {
+  xchg_finish_kernel<<<1, 32, 0, c.stream>>>(l, k, d_out);
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;

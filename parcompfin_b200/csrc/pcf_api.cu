@@ -11,6 +11,7 @@
 // NCCL is bound lazily through dlopen("libnccl.so.2") so that single-GPU use has no NCCL
 // dependency and a host process that already carries NCCL (PyTorch) shares its copy.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -22,12 +23,14 @@
 namespace pcf {
 
 // ---- method drivers implemented in the kernel files --------------------------------------------
-int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay);
-int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay);
-int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host, Shard paths, const double* d_replay);
-int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset);
+int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, const PeerLink& link);
+int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay, const PeerLink& link);
+int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host, Shard paths, const double* d_replay,
+                  const PeerLink& link);
+int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset,
+                PeerLink* final_link);
 size_t amer_workspace_bytes(long long local_pairs, int M);
-int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid);
+int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid, const PeerLink& link);
 void binom_lattice(double r, double sigma, double T, long long N, double& u, double& d, double& p, double& q);
 int run_philox_kat(Ctx& c, const unsigned int ctr[4], const unsigned int key[2], uint32_t* d_out);
 int run_normal_stream(Ctx& c, uint64_t seed, uint32_t stream, uint64_t index0, long long count, int T,
@@ -119,6 +122,14 @@ static int ctx_open(Ctx& c, int device, int rank, int world) {
   PCF_CUDA(cudaMemset(c.d_out, 0, sizeof(double) * 64));
   PCF_CUDA(cudaMemset(c.d_flag, 0, sizeof(int)));
   PCF_CUDA(cudaMallocHost(&c.h_out, sizeof(double) * 64));
+  PCF_CUDA(cudaMalloc(&c.mailbox, sizeof(Mailbox)));
+  PCF_CUDA(cudaMemset(c.mailbox, 0, sizeof(Mailbox)));
+  c.link = PeerLink{};
+  c.link.rank = rank;
+  c.link.world = world;
+  c.link.peer[rank] = c.mailbox;
+  c.peer_ok = false;
+  c.xchg_seq = 0;
   static MathTables host_tables;
   static std::once_flag once;
   std::call_once(once, [] { build_math_tables(host_tables); });
@@ -129,8 +140,13 @@ static int ctx_open(Ctx& c, int device, int rank, int world) {
   return PCF_OK;
 }
 
+static std::vector<void*> g_ipc_opened;
+
 static void ctx_close(Ctx& c) {
   cudaSetDevice(c.device);
+  for (void* ptr : g_ipc_opened) cudaIpcCloseMemHandle(ptr);
+  g_ipc_opened.clear();
+  if (c.mailbox) cudaFree(c.mailbox);
   if (c.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.comm);
   if (c.workspace) cudaFree(c.workspace);
   if (c.h_out) cudaFreeHost(c.h_out);
@@ -195,13 +211,22 @@ static int upload_replay(Ctx& c, const double* host, long long off, long long le
 }
 
 // Common tail of every method: [allreduce of k doubles] -> event -> D2H -> sync.
-static int finish_call(Ctx& c, int k, double* host_vals, double* seconds_kernel, int* flag) {
-  PCF_TRY(allreduce_sum(c, c.d_out, k));
+static int finish_call(Ctx& c, const PeerLink& link, int k, double* host_vals, double* seconds_kernel, int* flag) {
+  if (c.world > 1) {
+    if (use_peer(c)) PCF_TRY(launch_xchg_finish(c, link, k, c.d_out));  // waits on the mailbox flags, adds in rank order
+    else if (c.comm) PCF_TRY(allreduce_sum(c, c.d_out, k));
+    else { set_last_error("multi-GPU job without peer mapping or NCCL communicator"); return PCF_ENOINIT; }
+  }
   PCF_CUDA(cudaEventRecord(c.ev1, c.stream));
   PCF_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * k, cudaMemcpyDeviceToHost, c.stream));
-  int hflag = 0;
+  int hflag = 0, perr = 0;
   PCF_CUDA(cudaMemcpyAsync(&hflag, c.d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  if (use_peer(c)) PCF_CUDA(cudaMemcpyAsync(&perr, &c.mailbox->error, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   PCF_CUDA(cudaStreamSynchronize(c.stream));
+  if (perr) {
+    set_last_error("peer-memory exchange timed out waiting for another GPU");
+    return PCF_ENCCL;
+  }
   for (int i = 0; i < k; ++i) host_vals[i] = c.h_out[i];
   float ms = 0.f;
   PCF_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
@@ -270,18 +295,37 @@ int pcf_init(int gpus) {
     if (s != PCF_OK) { pcf_shutdown(); return s; }
   }
   if (gpus > 1) {
-    int s = nccl_load();
-    if (s != PCF_OK) { pcf_shutdown(); return s; }
-    std::vector<void*> comms(gpus);
-    std::vector<int> devs(gpus);
-    for (int i = 0; i < gpus; ++i) devs[i] = i;
-    int r = g_nccl.CommInitAll(comms.data(), gpus, devs.data());
-    if (r != 0) {
-      set_last_error(std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r));
-      pcf_shutdown();
-      return PCF_ENCCL;
+    // NVLink peer mapping of every GPU's mailbox (xchg.cuh); NCCL only when peer access is unavailable
+    bool peer = (gpus <= kMaxWorld) && !getenv("PCF_NO_PEER");
+    for (int i = 0; i < gpus && peer; ++i)
+      for (int j = 0; j < gpus && peer; ++j) {
+        if (i == j) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, i, j) != cudaSuccess || !can) { peer = false; break; }
+        cudaSetDevice(i);
+        cudaError_t e = cudaDeviceEnablePeerAccess(j, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peer = false;
+        cudaGetLastError();
+      }
+    if (peer) {
+      for (int i = 0; i < gpus; ++i) {
+        for (int r = 0; r < gpus; ++r) g_ctx[i].link.peer[r] = g_ctx[r].mailbox;
+        g_ctx[i].peer_ok = true;
+      }
+    } else {
+      int s = nccl_load();
+      if (s != PCF_OK) { pcf_shutdown(); return s; }
+      std::vector<void*> comms(gpus);
+      std::vector<int> devs(gpus);
+      for (int i = 0; i < gpus; ++i) devs[i] = i;
+      int r = g_nccl.CommInitAll(comms.data(), gpus, devs.data());
+      if (r != 0) {
+        set_last_error(std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r));
+        pcf_shutdown();
+        return PCF_ENCCL;
+      }
+      for (int i = 0; i < gpus; ++i) g_ctx[i].comm = comms[i];
     }
-    for (int i = 0; i < gpus; ++i) g_ctx[i].comm = comms[i];
   }
   return PCF_OK;
 }
@@ -306,8 +350,7 @@ int pcf_init_rank(int rank, int world, int device, const unsigned char* nccl_id)
   g_ctx.resize(1);
   int s = ctx_open(g_ctx[0], device, rank, world);
   if (s != PCF_OK) { pcf_shutdown(); return s; }
-  if (world > 1) {
-    if (!nccl_id) { pcf_shutdown(); return PCF_EINVAL; }
+  if (world > 1 && nccl_id) {  // NCCL communicator: the fallback when the mailboxes cannot be peer-mapped
     s = nccl_load();
     if (s != PCF_OK) { pcf_shutdown(); return s; }
     NcclId nid;
@@ -321,6 +364,46 @@ int pcf_init_rank(int rank, int world, int device, const unsigned char* nccl_id)
   }
   return PCF_OK;
 }
+
+int pcf_ipc_export(unsigned char handle[64]) {
+  if (g_ctx.size() != 1) return PCF_ENOINIT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  PCF_CUDA(cudaSetDevice(g_ctx[0].device));
+  cudaIpcMemHandle_t h;
+  PCF_CUDA(cudaIpcGetMemHandle(&h, g_ctx[0].mailbox));
+  std::memcpy(handle, &h, 64);
+  return PCF_OK;
+}
+
+int pcf_ipc_import(const unsigned char* handles, int world) {
+  if (g_ctx.size() != 1) return PCF_ENOINIT;
+  Ctx& c = g_ctx[0];
+  if (!handles || world != c.world || world > kMaxWorld) return PCF_EINVAL;
+  PCF_CUDA(cudaSetDevice(c.device));
+  for (int r = 0; r < world; ++r) {
+    if (r == c.rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 64 * r, 64);
+    void* ptr = nullptr;
+    PCF_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    g_ipc_opened.push_back(ptr);
+    c.link.peer[r] = (Mailbox*)ptr;
+  }
+  c.peer_ok = true;
+  return PCF_OK;
+}
+
+int pcf_peer_enable(int on) {
+  if (g_ctx.empty()) return PCF_ENOINIT;
+  for (auto& c : g_ctx) {
+    bool mapped = true;
+    for (int r = 0; r < c.world; ++r) mapped = mapped && c.link.peer[r] != nullptr;
+    c.peer_ok = on && mapped;
+  }
+  return (on && !g_ctx[0].peer_ok && g_ctx[0].world > 1) ? PCF_EINVAL : PCF_OK;
+}
+
+int pcf_peer_active(void) { return (!g_ctx.empty() && use_peer(g_ctx[0])) ? 1 : 0; }
 
 int pcf_shutdown(void) {
   for (auto& c : g_ctx) ctx_close(c);
@@ -348,8 +431,9 @@ int pcf_mc_eur(const pcf_params* p, pcf_result* out) {
       PCF_TRY(upload_replay(c, p->replay, off, end - off, 0, &d_rep));
     }
     PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
-    PCF_TRY(run_mc_eur(c, *p, sh, d_rep));
-    PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+    const PeerLink l = next_link(c);
+    PCF_TRY(run_mc_eur(c, *p, sh, d_rep, l));
+    PCF_TRY(finish_call(c, l, 2, o.vals, &o.seconds_kernel, &o.flag));
     o.launches = c.launches;
     return PCF_OK;
   });
@@ -372,8 +456,9 @@ int pcf_mc_asia(const pcf_params* p, pcf_result* out) {
     const double* d_rep = nullptr;
     if (p->replay) PCF_TRY(upload_replay(c, p->replay, sh.begin * p->M, sh.size() * p->M, 0, &d_rep));
     PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
-    PCF_TRY(run_mc_asia(c, *p, sh, d_rep));
-    PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+    const PeerLink l = next_link(c);
+    PCF_TRY(run_mc_asia(c, *p, sh, d_rep, l));
+    PCF_TRY(finish_call(c, l, 2, o.vals, &o.seconds_kernel, &o.flag));
     o.launches = c.launches;
     return PCF_OK;
   });
@@ -417,8 +502,9 @@ int pcf_mc_eur_multi(const pcf_params* p, pcf_result* out) {
     if (p->replay)
       PCF_TRY(upload_replay(c, p->replay, sh.begin * p->assets, sh.size() * p->assets, 0, &d_rep));
     PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
-    PCF_TRY(run_mc_basket(c, *p, L, sh, d_rep));
-    PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+    const PeerLink l = next_link(c);
+    PCF_TRY(run_mc_basket(c, *p, L, sh, d_rep, l));
+    PCF_TRY(finish_call(c, l, 2, o.vals, &o.seconds_kernel, &o.flag));
     o.launches = c.launches;
     return PCF_OK;
   });
@@ -445,8 +531,9 @@ int pcf_mc_amer(const pcf_params* p, pcf_result* out) {
     const double* d_rep = nullptr;
     if (p->replay) PCF_TRY(upload_replay(c, p->replay, sh.begin * p->M, sh.size() * p->M, 0, &d_rep));
     PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
-    PCF_TRY(run_mc_amer(c, *p, sh, d_rep, rep_bytes));
-    PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+    PeerLink l;
+    PCF_TRY(run_mc_amer(c, *p, sh, d_rep, rep_bytes, &l));
+    PCF_TRY(finish_call(c, l, 2, o.vals, &o.seconds_kernel, &o.flag));
     o.launches = c.launches;
     return PCF_OK;
   });
@@ -486,8 +573,9 @@ int pcf_binom_embar(const pcf_params* p, pcf_result* out) {
     Shard sh = shard_of(until - lo, c.rank, c.world);
     sh.begin += lo; sh.end += lo;
     PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
-    PCF_TRY(run_binom(c, *p, sh, (p->N % 2 == 0) && c.rank == 0));
-    PCF_TRY(finish_call(c, 1, o.vals, &o.seconds_kernel, &o.flag));
+    const PeerLink l = next_link(c);
+    PCF_TRY(run_binom(c, *p, sh, (p->N % 2 == 0) && c.rank == 0, l));
+    PCF_TRY(finish_call(c, l, 1, o.vals, &o.seconds_kernel, &o.flag));
     o.launches = c.launches;
     return PCF_OK;
   });

@@ -4,6 +4,7 @@
 // OpenMP `reduction(+:result)` / MPI_Reduce (src/mc_eur_omp.cpp, src/mc_eur_mpi.cpp:36).
 #pragma once
 #include <cstdint>
+#include "xchg.cuh"
 
 namespace pcf {
 
@@ -91,9 +92,11 @@ __device__ __forceinline__ void block_reduce(Comp (&v)[K], double* smem) {
 // block to arrive (ticket counter) folds all partials in block order and writes out[k] = hi+lo.
 // `ticket` must be zero on entry and is reset to zero on exit, so the buffer is reusable across
 // launches on the same stream. smem as for block_reduce.
+// When `link` names a multi-GPU job (world > 1) the last block also publishes the K sums to every peer's mailbox
+// (xchg.cuh): the reduction and the collective are one kernel.
 template <int K>
 __device__ __forceinline__ void grid_reduce(Comp (&v)[K], double* smem, double* partials,
-                                            unsigned int* ticket, double* out) {
+                                            unsigned int* ticket, double* out, const PeerLink* link = nullptr) {
   block_reduce<K>(v, smem);
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
@@ -119,10 +122,19 @@ __device__ __forceinline__ void grid_reduce(Comp (&v)[K], double* smem, double* 
   }
   __syncthreads();  // smem reuse
   block_reduce<K>(acc, smem);
+  __syncthreads();  // smem reuse below
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) out[k] = acc[k].value();
+    for (int k = 0; k < K; ++k) {
+      const double r = acc[k].value();
+      out[k] = r;
+      smem[k] = r;
+    }
     *ticket = 0u;
+  }
+  if (link != nullptr && link->world > 1) {
+    __syncthreads();
+    peer_publish<K>(*link, smem);
   }
 }
 

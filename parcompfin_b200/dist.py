@@ -88,3 +88,18 @@ def init_library(job: Job) -> None:
         return
     nid = share_bytes(job, pcf.nccl_unique_id() if job.rank == 0 else None)
     pcf.init_rank(job.rank, job.world, job.local_rank, nid)
+    # NVLink peer-memory exchange: all-gather the 64-byte CUDA IPC handles of the mailboxes; every rank must
+    # succeed, otherwise the whole job stays on the NCCL all-reduce path.
+    if os.environ.get("PCF_NO_PEER"):
+        return
+    import torch.distributed as td
+    ok = 1.0
+    try:
+        handles = [None] * job.world
+        td.all_gather_object(handles, pcf.ipc_export())
+        pcf.ipc_import(handles)
+    except Exception:  # noqa: BLE001 -- IPC not permitted in this environment
+        ok = 0.0
+    any_fail = reduce_scalars(job, [1.0 - ok], "max")[0] > 0
+    if any_fail:
+        pcf.peer_enable(False)

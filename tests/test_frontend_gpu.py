@@ -1,0 +1,61 @@
+"""GPU tests of the drop-in executables (bin/*): same argv, same CSV row as the reference programs."""
+import math
+import os
+import subprocess
+
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "bin")
+
+
+def run(prog, *args, env=None):
+    e = dict(os.environ, **(env or {}))
+    p = subprocess.run([os.path.join(BIN, prog), *map(str, args)], env=e, capture_output=True, text=True)
+    return p.returncode, p.stdout.strip(), p.stderr
+
+
+def test_row_format_matches_reference_layout(tmp_path):
+    # reference row: include/common.h:212-249 -- 16 comma-separated fields, setprecision(10)
+    N, M = 20000, 252
+    w = oracle.normals_mt19937(42, math.sqrt(1 / M), N * M)
+    f = tmp_path / "w.f64"
+    w.tofile(f)
+    rc, out, err = run("mc_asia", "call", 100, 100, 0.05, 0.2, 1, N, M, 1, env={"PCF_REPLAY": str(f), "PCF_COMPARISON": "5.5"})
+    assert rc == 0, err
+    fields = out.split(",")
+    assert len(fields) == 16 and len(out.splitlines()) == 1
+    assert fields[:11] == ["CUDA", "call", "100", "100", "0.05", "0.2", "1", str(N), str(M), "1", "1"]
+    want = oracle.mc_asia(100, 100, .05, .2, 1, N, M, "call", w)
+    assert fields[13] == f"{want:.10g}"
+    assert fields[14] == f"{abs(want - 5.5):.10g}" and fields[15] == f"{want - 5.5:.10g}"
+    if oracle.have_ref():
+        ref = oracle.ref_row("mc_asia", "call", 100, 100, 0.05, 0.2, 1, N, M, seed=42)
+        assert ref[1:9] == fields[1:9] and ref[10] == fields[10] and ref[13] == fields[13]
+
+
+@pytest.mark.parametrize("prog,args,nfield", [
+    ("mc_eur", ("put", 100, 100, 0.05, 0.2, 1, 100000), ("0", "1")),
+    ("mc_amer", ("put", 100, 100, 0.05, 0.2, 1, 100000, 50), ("50", "1")),
+    ("mc_eur_multi", ("call", 100, 100, 0.05, 0.2, 1, 100000, 16, 0.5), ("0", "16")),
+    ("binom_embar", ("call", 100, 110, 0.02, 0.75, 1, 1000), ("0", "1")),
+])
+def test_every_front_end_prints_one_row(prog, args, nfield):
+    rc, out, err = run(prog, *args, env={"PCF_SEED": "7"})
+    assert rc == 0, err
+    fields = out.split(",")
+    assert len(fields) == 16 and fields[0] == "CUDA" and fields[1] == args[0]
+    assert (fields[8], fields[10]) == nfield
+    assert math.isfinite(float(fields[13]))
+    if prog == "binom_embar":
+        assert fields[13] == "26.60882645"  # reference results/results_binom_embar.csv, N = 1000
+
+
+def test_error_behaviour_matches_reference():
+    rc, out, err = run("mc_eur", "straddle", 100, 100, 0.05, 0.2, 1, 1000)
+    assert rc != 0 and out == "" and "Unknown payoff function" in err      # src/mc_eur.cpp:42
+    rc, out, err = run("mc_amer", "put", 100, 100, 0.05, 0.2, 1, 1001, 10)
+    assert rc != 0 and out == "" and "divisible by 2" in err              # include/common.h:180
