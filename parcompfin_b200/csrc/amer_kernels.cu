@@ -13,10 +13,15 @@
 // exercise_st of the reference is a pure function of (cash, flag): st = flag ? payoff(cp*cash, E)
 // : cash, because cp*cash == S - E exactly for an in-the-money path.
 //
-// Per exercise date: moments kernel (HBM-bound: 8 B S + 12 B state per path) -> [ncclAllReduce of
-// 8 doubles when the job has several GPUs] -> decision kernel (8 B S re-read + 12 B state write for
-// exercising paths); the 3x3 normal equations are solved on the device by every block, in the
-// reference's operation order and without FMA contraction.
+// Rows and state arrays are padded to a multiple of 4 paths (Np) with never-in-the-money dummies so that every
+// thread streams whole 32-byte sectors (4 paths) with 16-byte vector loads/stores.
+//
+// Backward sweep: ONE fused kernel per exercise date. amer_sweep_kernel for date m (a) waits for the moments of
+// date m (its own, or -- multi-GPU -- every rank's, arriving in the NVLink mailbox), solves the 3x3 normal
+// equations per block in the reference's operation order without FMA contraction, (b) applies the exercise
+// decision of date m to the state held in registers, (c) accumulates the regression moments of date m-1 from
+// that updated state and row m-1, and (d) its last block publishes them. Compared with a moments pass plus a
+// decision pass this reads the 12 B/path state once per date instead of twice and halves the launches.
 #include "common.cuh"
 #include "reduce.cuh"
 #include "rng.cuh"
@@ -38,6 +43,7 @@ struct AmerArgs {
   int cp, M;
   long long p0;       // first global pair of this GPU
   long long H;        // local pairs; Nl = 2H
+  long long Np;       // padded row length (multiple of 4)
   unsigned long long seed;
   const double* w;    // replay: w[(p-p0)*M + (m-1)]
 };
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, cons
   Hoisted hc;
   hc.load();
   const PhiloxKey key(a.seed);
-  const long long Nl = 2 * a.H;
+  const long long Nl = a.Np;  // row stride
   const double ea = a.exp_adt;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.H;
        p += (long long)gridDim.x * blockDim.x) {
@@ -103,71 +109,20 @@ __global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, cons
   }
 }
 
-// a7 pass 1 (mc_amer.cpp:41-59): moments over in-the-money paths at date m.
-// out[0..7] = n_itm, Sx, Sx^2, Sx^3, Sx^4, Sy, Syx, Syx^2. Products are formed exactly like the
-// reference forms them (left to right, no FMA) so that only the summation order differs.
-// HBM-bound: each thread streams two paths per iteration (16 B vector loads of S, state loads only for
-// in-the-money lanes); the eight sums run as plain FP64 adds over kMomFold iterations and are then folded
-// into compensated totals, so the compensation costs ~1 add per path instead of 7.
-constexpr int kMomFold = 8;
-
-__device__ __forceinline__ void amer_moment_terms(double S, int wq, double cs, double E, int cp, int m,
-                                                  const double* s_disc, double (&run)[8]) {
-  if (payoff(S, E, cp) > 0.0) {
-    const double ex = __dadd_rn(S, -E);
-    const double cont = __dmul_rn(s_disc[(wq & ~kQuirkBit) - m], cs);
-    const double ex2 = __dmul_rn(ex, ex), ex3 = __dmul_rn(ex2, ex), ex4 = __dmul_rn(ex3, ex);
-    const double yx = __dmul_rn(cont, ex), yx2 = __dmul_rn(yx, ex);
-    run[0] += 1.0;
-    run[1] += ex;
-    run[2] += ex2;
-    run[3] += ex3;
-    run[4] += ex4;
-    run[5] += cont;
-    run[6] += yx;
-    run[7] += yx2;
-  }
-}
-
-__global__ void __launch_bounds__(kAmerBlock) amer_moments_kernel(
-    const double* __restrict__ S_row, const int* __restrict__ when, const double* __restrict__ cash,
-    long long Nl, double E, int cp, int m, int M, PeerLink link, double* partials, unsigned int* ticket,
-    double* out) {
-  __shared__ double smem[8 * 2 * 32];
-  extern __shared__ double s_disc[];  // lanes index it with different k: shared memory, not constant
-  for (int k = threadIdx.x; k <= M; k += blockDim.x) s_disc[k] = c_disc_fwd[k];
-  __syncthreads();
-  Comp acc[8];
-  double run[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int fold = 0;
-  const long long pairs = Nl >> 1;  // Nl is even
-  const double2* S2 = reinterpret_cast<const double2*>(S_row);
-  const int2* W2 = reinterpret_cast<const int2*>(when);
-  const double2* C2 = reinterpret_cast<const double2*>(cash);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs;
+// Padding columns [2H, Np): S chosen so that payoff == 0 at every date, state = (M, 0).
+__global__ void amer_pad_kernel(double* __restrict__ paths, int* __restrict__ when, double* __restrict__ cash,
+                                long long Nl, long long Np, int M, int cp) {
+  const long long pad = Np - Nl;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pad * (M + 1);
        i += (long long)gridDim.x * blockDim.x) {
-    const double2 S = __ldcs(S2 + i);
-    const bool itm0 = payoff(S.x, E, cp) > 0.0, itm1 = payoff(S.y, E, cp) > 0.0;
-    int2 w = make_int2(0, 0);
-    double2 c = make_double2(0.0, 0.0);
-    if (itm0 || itm1) {
-      w = W2[i];
-      c = C2[i];
-    }
-    amer_moment_terms(S.x, w.x, c.x, E, cp, m, s_disc, run);
-    amer_moment_terms(S.y, w.y, c.y, E, cp, m, s_disc, run);
-    if (++fold == kMomFold) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        acc[k].add(run[k]);
-        run[k] = 0.0;
-      }
-      fold = 0;
+    const long long row = i / pad, col = Nl + i % pad;
+    if (row < M) {
+      paths[row * Np + col] = cp > 0 ? 0.0 : 1e300;  // call: S - E < 0;  put: E - S < 0
+    } else {
+      when[col] = M;
+      cash[col] = 0.0;
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k].add(run[k]);
-  grid_reduce<8>(acc, smem, partials, ticket, out, &link);
 }
 
 // a8: include/common.h:98-141 in the reference's operation order (cyclic %3 indexing, adjugate /
@@ -197,73 +152,155 @@ __device__ bool solve3_reference_order(const double* mom, double coef[3]) {
   return true;
 }
 
-// a7 pass 2 (mc_amer.cpp:73-106): exercise decision at date m from the (all-reduced) moments.
-__global__ void __launch_bounds__(kAmerBlock) amer_decide_kernel(
-    const double* __restrict__ S_row, int* __restrict__ when, double* __restrict__ cash, long long Nl,
-    double E, int cp, int m, const double* __restrict__ mom_local, PeerLink link, int* err_flag) {
-  __shared__ double s_coef[3];
-  __shared__ double s_mom[kXchgVals];
-  __shared__ int s_mode;  // 0 skip, 1 few-paths branch, 2 regression branch
-  // Multi-GPU: the moments of every rank arrive in this GPU's mailbox (published by the last block of each rank's
-  // moments kernel); wait for them here instead of running a collective between the two passes.
-  if (link.world > 1) {
-    peer_gather<kXchgVals>(link, s_mom);
+// a7 (mc_amer.cpp:41-106), one fused kernel per date; see the file header.
+//   kDecide:  apply the exercise decision of date m (rows S_m) from the moments of date m
+//   kMoments: accumulate the moments of date m-1 (rows S_prev) and publish them
+// out[0..7] = n_itm, Sx, Sx^2, Sx^3, Sx^4, Sy, Syx, Syx^2 with x = S - E, y = discounted cash flow; products
+// are formed exactly like the reference forms them (left to right, no FMA): only the summation order differs.
+constexpr int kMomFold = 4;
+
+__device__ __forceinline__ void amer_decide_one(double S, int& wq, double& cs, bool& changed, int mode, double c0,
+                                                double c1, double c2, double E, int cp, int m,
+                                                const double* s_disc) {
+  const double pv = payoff(S, E, cp);
+  if (!(pv > 0.0)) return;
+  if (mode == 2) {
+    const double x = __dadd_rn(S, -E);
+    if (x == -1.0) return;  // the reference's sentinel collision (mc_amer.cpp:32,98)
+    const double yhat = __dadd_rn(__dadd_rn(c0, __dmul_rn(c1, x)), __dmul_rn(c2, __dmul_rn(x, x)));
+    const double pq = payoff(x, E, cp);  // payoff of the SHIFTED value (mc_amer.cpp:100)
+    if (pq > yhat) {
+      wq = m | kQuirkBit;
+      cs = pv;
+      changed = true;
+    }
   } else {
-    if (threadIdx.x < kXchgVals) s_mom[threadIdx.x] = mom_local[threadIdx.x];
-    __syncthreads();
+    // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against the discounted cash flow
+    const double cont = __dmul_rn(s_disc[(wq & ~kQuirkBit) - m], cs);
+    if (pv > cont) {
+      wq = m;
+      cs = pv;
+      changed = true;
+    }
   }
-  const double* mom = s_mom;
-  if (threadIdx.x == 0) {
-    double cnt = mom[0];
-    if (cnt == 0.0) {
-      s_mode = 0;
-    } else if (cnt <= 2.0) {
-      s_mode = 1;
+}
+
+__device__ __forceinline__ void amer_moment_terms(double S, int wq, double cs, double E, int cp, int m,
+                                                  const double* s_disc, double (&run)[8]) {
+  if (payoff(S, E, cp) > 0.0) {
+    const double ex = __dadd_rn(S, -E);
+    const double cont = __dmul_rn(s_disc[(wq & ~kQuirkBit) - m], cs);
+    const double ex2 = __dmul_rn(ex, ex), ex3 = __dmul_rn(ex2, ex), ex4 = __dmul_rn(ex3, ex);
+    const double yx = __dmul_rn(cont, ex), yx2 = __dmul_rn(yx, ex);
+    run[0] += 1.0;
+    run[1] += ex;
+    run[2] += ex2;
+    run[3] += ex3;
+    run[4] += ex4;
+    run[5] += cont;
+    run[6] += yx;
+    run[7] += yx2;
+  }
+}
+
+template <bool kDecide, bool kMoments>
+__global__ void __launch_bounds__(kAmerBlock, 2) amer_sweep_kernel(
+    const double* __restrict__ S_m, const double* __restrict__ S_prev, int* __restrict__ when,
+    double* __restrict__ cash, long long Np, double E, int cp, int m, int M,
+    const double* __restrict__ mom_in, PeerLink link_in, PeerLink link_out, double* partials,
+    unsigned int* ticket, double* mom_out, int* err_flag) {
+  __shared__ double smem[8 * 2 * 32];
+  __shared__ double s_mom[kXchgVals];
+  __shared__ double s_coef[3];
+  __shared__ int s_mode;  // 0 skip, 1 few-paths branch, 2 regression branch
+  extern __shared__ double s_disc[];  // lanes index it with different k: shared memory, not constant
+  for (int k = threadIdx.x; k <= M; k += blockDim.x) s_disc[k] = c_disc_fwd[k];
+  int mode = 0;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  if (kDecide) {
+    // moments of date m: from every rank's publication in this GPU's mailbox (multi-GPU), else local / all-reduced
+    if (link_in.world > 1) {
+      peer_gather<kXchgVals>(link_in, s_mom);
     } else {
-      double coef[3];
-      if (solve3_reference_order(mom, coef)) {
-        s_mode = 2;
-        s_coef[0] = coef[0]; s_coef[1] = coef[1]; s_coef[2] = coef[2];
+      if (threadIdx.x < kXchgVals) s_mom[threadIdx.x] = mom_in[threadIdx.x];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const double cnt = s_mom[0];
+      if (cnt == 0.0) {
+        s_mode = 0;                       // mc_amer.cpp:73
+      } else if (cnt <= 2.0) {
+        s_mode = 1;                       // mc_amer.cpp:75
       } else {
-        s_mode = 0;
-        if (blockIdx.x == 0) atomicExch(err_flag, PCF_ESINGULAR);
+        double coef[3];
+        if (solve3_reference_order(s_mom, coef)) {
+          s_mode = 2;
+          s_coef[0] = coef[0]; s_coef[1] = coef[1]; s_coef[2] = coef[2];
+        } else {
+          s_mode = 0;
+          if (blockIdx.x == 0) atomicExch(err_flag, PCF_ESINGULAR);  // common.h:115-117
+        }
       }
     }
   }
   __syncthreads();
-  const int mode = s_mode;
-  if (mode == 0) return;
-  const double c0 = s_coef[0], c1 = s_coef[1], c2 = s_coef[2];
-  const long long pairs = Nl >> 1;
-  const double2* S2 = reinterpret_cast<const double2*>(S_row);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs;
+  if (kDecide) {
+    mode = s_mode;
+    c0 = s_coef[0]; c1 = s_coef[1]; c2 = s_coef[2];
+  }
+  Comp acc[8];
+  double run[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int fold = 0;
+  const long long quads = Np >> 2;
+  const double2* Sm2 = reinterpret_cast<const double2*>(S_m);
+  const double2* Sp2 = reinterpret_cast<const double2*>(S_prev);
+  int4* W4 = reinterpret_cast<int4*>(when);
+  double2* C2 = reinterpret_cast<double2*>(cash);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads;
        i += (long long)gridDim.x * blockDim.x) {
-    const double2 S2v = __ldcs(S2 + i);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const double S = h ? S2v.y : S2v.x;
-      const long long n = 2 * i + h;
-      const double pv = payoff(S, E, cp);
-      if (!(pv > 0.0)) continue;
-      if (mode == 2) {
-        const double x = __dadd_rn(S, -E);
-        if (x == -1.0) continue;  // the reference's sentinel collision (mc_amer.cpp:32,98)
-        const double yhat = __dadd_rn(__dadd_rn(c0, __dmul_rn(c1, x)), __dmul_rn(c2, __dmul_rn(x, x)));
-        const double pq = payoff(x, E, cp);  // payoff of the SHIFTED value (mc_amer.cpp:100)
-        if (pq > yhat) {
-          when[n] = m | kQuirkBit;
-          cash[n] = pv;
-        }
-      } else {
-        // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against discounted cash flow
-        const int k = (when[n] & ~kQuirkBit) - m;
-        const double cont = __dmul_rn(c_disc_fwd[k], cash[n]);
-        if (pv > cont) {
-          when[n] = m;
-          cash[n] = pv;
-        }
+    // 7 independent 16-byte loads per thread: one 32-byte sector of each row, the state of 4 paths
+    double2 sa = make_double2(0, 0), sb = sa, pa = sa, pb = sa;
+    if (kDecide) {
+      sa = __ldcs(Sm2 + 2 * i);
+      sb = __ldcs(Sm2 + 2 * i + 1);
+    }
+    if (kMoments) {
+      pa = __ldcs(Sp2 + 2 * i);
+      pb = __ldcs(Sp2 + 2 * i + 1);
+    }
+    int4 w = W4[i];
+    double2 ca = C2[2 * i], cb = C2[2 * i + 1];
+    if (kDecide && mode != 0) {
+      bool changed = false;
+      amer_decide_one(sa.x, w.x, ca.x, changed, mode, c0, c1, c2, E, cp, m, s_disc);
+      amer_decide_one(sa.y, w.y, ca.y, changed, mode, c0, c1, c2, E, cp, m, s_disc);
+      amer_decide_one(sb.x, w.z, cb.x, changed, mode, c0, c1, c2, E, cp, m, s_disc);
+      amer_decide_one(sb.y, w.w, cb.y, changed, mode, c0, c1, c2, E, cp, m, s_disc);
+      if (changed) {  // whole sectors back: no partial-sector fill from DRAM
+        W4[i] = w;
+        C2[2 * i] = ca;
+        C2[2 * i + 1] = cb;
       }
     }
+    if (kMoments) {
+      amer_moment_terms(pa.x, w.x, ca.x, E, cp, m - 1, s_disc, run);
+      amer_moment_terms(pa.y, w.y, ca.y, E, cp, m - 1, s_disc, run);
+      amer_moment_terms(pb.x, w.z, cb.x, E, cp, m - 1, s_disc, run);
+      amer_moment_terms(pb.y, w.w, cb.y, E, cp, m - 1, s_disc, run);
+      if (++fold == kMomFold) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc[k].add(run[k]);
+          run[k] = 0.0;
+        }
+        fold = 0;
+      }
+    }
+  }
+  if (kMoments) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k].add(run[k]);
+    grid_reduce<8>(acc, smem, partials, ticket, mom_out, &link_out);
   }
 }
 
@@ -311,16 +348,17 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   PCF_CUDA(cudaMemcpyToSymbolAsync(c_disc_fwd, fwd, sizeof(double) * (M + 1), 0, cudaMemcpyHostToDevice, c.stream));
   PCF_CUDA(cudaMemcpyToSymbolAsync(c_disc_abs, ab, sizeof(double) * (M + 1), 0, cudaMemcpyHostToDevice, c.stream));
 
+  const long long Np = (Nl + 3) & ~3LL;  // padded row length
   char* base = (char*)c.workspace + ws_offset;
   double* paths = (double*)base;
-  double* cash = paths + (size_t)M * Nl;
-  int* when = (int*)(cash + Nl);
+  double* cash = paths + (size_t)M * Np;
+  int* when = (int*)(cash + Np);
 
   AmerArgs a;
   a.S0 = p.S0; a.E = p.E; a.cp = p.cp; a.M = M;
   a.adt = (p.r - 0.5 * p.sigma * p.sigma) * dt;
   a.cs = d_replay ? p.sigma : p.sigma * sqrt(dt);
-  a.p0 = pairs.begin; a.H = H; a.seed = p.seed; a.w = d_replay;
+  a.p0 = pairs.begin; a.H = H; a.Np = Np; a.seed = p.seed; a.w = d_replay;
 
   a.exp_adt = exp(a.adt);
   const bool small = fabs(a.cs) * kZMax <= kSmallExpBound;
@@ -332,32 +370,55 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   else
     amer_paths_kernel<false, false><<<grid_gen, kAmerBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, paths, when, cash);
   c.launches++;
+  if (Np != Nl) {
+    amer_pad_kernel<<<1, 128, 0, c.stream>>>(paths, when, cash, Nl, Np, M, p.cp);
+    c.launches++;
+  }
   PCF_CUDA(cudaGetLastError());
 
-  int grid = grid_for(c, Nl, kAmerBlock, 8);
-  double* mom = c.d_out + 8;
-  for (int m = M - 1; m > 0; --m) {
-    const double* row = paths + (size_t)(m - 1) * Nl;
-    // peer path: the moments kernel publishes into every GPU's mailbox and the decision kernel waits on it;
-    // NCCL path (no peer mapping): an all-reduce of the 8 doubles between the two kernels.
-    const PeerLink l = next_link(c);
-    amer_moments_kernel<<<grid, kAmerBlock, sizeof(double) * (M + 1), c.stream>>>(
-        row, when, cash, Nl, p.E, p.cp, m, M, l, c.d_partials, c.d_ticket, mom);
-    if (!use_peer(c)) PCF_TRY(allreduce_sum(c, mom, 8));
-    amer_decide_kernel<<<grid, kAmerBlock, 0, c.stream>>>(row, when, cash, Nl, p.E, p.cp, m, mom, l, c.d_flag);
-    c.launches += 2;
+  // Backward sweep m = M-1 .. 1 (mc_amer.cpp:31). Kernel for date m consumes the moments of date m and produces
+  // those of date m-1. Peer path: moments travel through the NVLink mailboxes (publish in the producing kernel,
+  // gather in the consuming one); NCCL path: an all-reduce of the 8 doubles between two kernels.
+  int grid = grid_for(c, Np / 4, kAmerBlock, 2);
+  const size_t dsm = sizeof(double) * (M + 1);
+  double* mom[2] = {c.d_out + 8, c.d_out + 16};
+  auto row = [&](int m) { return paths + (size_t)(m - 1) * Np; };
+  PeerLink none = c.link;
+  none.world = 1;
+  if (M >= 2) {
+    PeerLink l_out = next_link(c);
+    amer_sweep_kernel<false, true><<<grid, kAmerBlock, dsm, c.stream>>>(
+        nullptr, row(M - 1), when, cash, Np, p.E, p.cp, M, M, nullptr, none, l_out, c.d_partials, c.d_ticket,
+        mom[(M - 1) & 1], c.d_flag);
+    c.launches++;
+    for (int m = M - 1; m >= 1; --m) {
+      const PeerLink l_in = l_out;
+      if (!use_peer(c)) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));
+      if (m > 1) {
+        l_out = next_link(c);
+        amer_sweep_kernel<true, true><<<grid, kAmerBlock, dsm, c.stream>>>(
+            row(m), row(m - 1), when, cash, Np, p.E, p.cp, m, M, mom[m & 1], l_in, l_out, c.d_partials,
+            c.d_ticket, mom[(m - 1) & 1], c.d_flag);
+      } else {
+        amer_sweep_kernel<true, false><<<grid, kAmerBlock, dsm, c.stream>>>(
+            row(1), nullptr, when, cash, Np, p.E, p.cp, 1, M, mom[1], l_in, none, c.d_partials, c.d_ticket,
+            nullptr, c.d_flag);
+      }
+      c.launches++;
+    }
   }
   *final_link = next_link(c);
-  amer_final_kernel<<<grid, kAmerBlock, sizeof(double) * (M + 1), c.stream>>>(when, cash, Nl, p.E, p.cp, M, *final_link,
-                                                                               c.d_partials, c.d_ticket, c.d_out);
+  int grid_fin = grid_for(c, Np, kAmerBlock, 8);
+  amer_final_kernel<<<grid_fin, kAmerBlock, dsm, c.stream>>>(when, cash, Np, p.E, p.cp, M, *final_link,
+                                                            c.d_partials, c.d_ticket, c.d_out);
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
 }
 
 size_t amer_workspace_bytes(long long local_pairs, int M) {
-  size_t Nl = 2 * (size_t)local_pairs;
-  return (size_t)M * Nl * 8 + Nl * 8 + Nl * 4 + 256;
+  size_t Np = (2 * (size_t)local_pairs + 3) & ~(size_t)3;
+  return (size_t)M * Np * 8 + Np * 8 + Np * 4 + 256;
 }
 
 }  // namespace pcf

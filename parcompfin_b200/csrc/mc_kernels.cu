@@ -23,35 +23,45 @@ struct EurArgs {
   const double* w;    // replay: w[n - 2*k0], already N(0,T)
 };
 
-template <bool kReplay, bool kSmallExp>
-__global__ void __launch_bounds__(kBlock) mc_eur_kernel(EurArgs a, const MathTables* __restrict__ tables, PeerLink link,
-                                                        double* partials, unsigned int* ticket, double* out) {
+// kPairs Philox blocks (2*kPairs paths) per thread iteration: independent integer and FP64 instruction streams
+// in one loop body (see mc_asia_kernel); sums are folded into the compensated totals once per iteration.
+template <bool kReplay, bool kSmallExp, int kPairs>
+__global__ void __launch_bounds__(kBlock, 1) mc_eur_kernel(EurArgs a, const MathTables* __restrict__ tables, PeerLink link,
+                                                           double* partials, unsigned int* ticket, double* out) {
   __shared__ double smem[2 * 2 * 32];
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
   Hoisted hc;
   hc.load();
   const PhiloxKey key(a.seed);
-  BlockedComp<4> s1, s2;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long k = a.k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < a.k1; k += stride) {
-    double w0, w1;
-    const bool has2 = (2 * k + 1 < a.N);
-    if (kReplay) {
-      w0 = a.w[2 * (k - a.k0)];
-      w1 = has2 ? a.w[2 * (k - a.k0) + 1] : 0.0;
-    } else {
-      double z0, z1;
-      normal_pair(key, (uint64_t)k, 0u, PCF_STREAM_EUR, tv, hc, z0, z1);
-      w0 = a.sqrtT * z0;
-      w1 = a.sqrtT * z1;
+  Comp s1, s2;
+  const long long T = (long long)gridDim.x * blockDim.x;
+  const double S0 = a.S0, E = a.E, sig = kReplay ? a.sigma : a.sigma * a.sqrtT, drift = a.drift;
+  const int cp = a.cp;
+  for (long long base = a.k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; base < a.k1; base += T * kPairs) {
+    double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < kPairs; ++q) {
+      const long long k = base + q * T;
+      const bool has1 = k < a.k1, has2 = has1 && (2 * k + 1 < a.N);
+      double w0, w1;
+      if (kReplay) {
+        w0 = has1 ? a.w[2 * (k - a.k0)] : 0.0;
+        w1 = has2 ? a.w[2 * (k - a.k0) + 1] : 0.0;
+      } else {
+        normal_pair(key, (uint64_t)k, 0u, PCF_STREAM_EUR, tv, hc, w0, w1);  // sqrt(T) folded into `sig`
+      }
+      double v0 = payoff(S0 * exp_any<kSmallExp>(fma(sig, w0, drift), tv, hc), E, cp);  // mc_eur.cpp:24
+      double v1 = payoff(S0 * exp_any<kSmallExp>(fma(sig, w1, drift), tv, hc), E, cp);
+      v0 = has1 ? v0 : 0.0;
+      v1 = has2 ? v1 : 0.0;
+      t1 += v0 + v1;
+      t2 = fma(v0, v0, fma(v1, v1, t2));
     }
-    double v0 = payoff(a.S0 * exp_any<kSmallExp>(fma(a.sigma, w0, a.drift), tv, hc), a.E, a.cp);
-    double v1 = has2 ? payoff(a.S0 * exp_any<kSmallExp>(fma(a.sigma, w1, a.drift), tv, hc), a.E, a.cp) : 0.0;
-    s1.add(v0 + v1);
-    s2.add(fma(v0, v0, v1 * v1));
+    s1.add(t1);
+    s2.add(t2);
   }
-  Comp v[2] = {s1.finish(), s2.finish()};
+  Comp v[2] = {s1, s2};
   grid_reduce<2>(v, smem, partials, ticket, out, &link);
 }
 
@@ -62,14 +72,18 @@ int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay,
   a.sqrtT = sqrt(p.T);
   a.k0 = pairs.begin; a.k1 = pairs.end;
   a.seed = p.seed; a.w = d_replay;
-  int grid = grid_for(c, pairs.size(), kBlock, kBlocksPerSM);
+  constexpr int kP = 4;
   const bool small = fabs(a.drift) + fabs(a.sigma * a.sqrtT) * kZMax <= kSmallExpBound;
-  if (d_replay)
-    mc_eur_kernel<true, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
-  else if (small)
-    mc_eur_kernel<false, true><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
-  else
-    mc_eur_kernel<false, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+  if (d_replay) {
+    int grid = grid_for(c, pairs.size(), kBlock, 2);
+    mc_eur_kernel<true, false, 1><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+  } else {
+    int grid = grid_for(c, (pairs.size() + kP - 1) / kP, kBlock, 1);
+    if (small)
+      mc_eur_kernel<false, true, kP><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+    else
+      mc_eur_kernel<false, false, kP><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+  }
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
@@ -210,7 +224,7 @@ int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay
   } else {
     // launch shape: PCF_ASIA_VARIANT = <paths per thread><min blocks per SM>, e.g. "14", "23" (tuning knob)
     const char* v = getenv("PCF_ASIA_VARIANT");
-    const int variant = v ? atoi(v) : 41;
+    const int variant = v ? atoi(v) : 61;
 #define PCF_ASIA_CASE(P, B)                                   \
   case P * 10 + B:                                            \
     if (small) launch_asia<true, P, B>(c, a, paths.size(), link);   \
@@ -305,6 +319,72 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const M
   grid_reduce<2>(v, smem, partials, ticket, out, &link);
 }
 
+// Equicorrelation fast path. The Cholesky factor of (1-rho) I + rho 11^T has constant columns below the
+// diagonal, L[a][k] = c_k for every a > k (include/mvn.h:55-70 builds exactly this matrix), so
+//   Bt[a] = (sum_{k<a} c_k z_k) + L[a][a] z_a
+// and the running prefix is the SAME chain of FMAs the general row-by-row product performs (bit-identical
+// result), at 2 FMAs per asset instead of (a+1). No per-path array is needed, which leaves the registers for
+// kPaths independent paths per thread.
+__constant__ double c_Lc[PCF_MAX_ASSETS];  // c_k  = L[k+1][k]
+__constant__ double c_Ld[PCF_MAX_ASSETS];  // d_a  = L[a][a]
+
+template <int kPaths>
+__global__ void __launch_bounds__(kBlock, 1) mc_basket_equi_kernel(BasketArgs a, const MathTables* __restrict__ tables,
+                                                                   PeerLink link, double* partials,
+                                                                   unsigned int* ticket, double* out) {
+  __shared__ double smem[2 * 2 * 32];
+  extern __shared__ __align__(16) unsigned char tab_smem[];
+  const TableView tv = stage_tables(tables, tab_smem);
+  Hoisted hc;
+  hc.load();
+  const PhiloxKey key(a.seed);
+  Comp s1, s2;
+  const long long T = (long long)gridDim.x * blockDim.x;
+  const double sigma = a.sigma, drift = a.drift, wS0 = a.wS0;
+  const int d = a.d;
+  for (long long base = a.n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; base < a.n1; base += T * kPaths) {
+    double prefix[kPaths], basket[kPaths];
+    uint32_t lo[kPaths], hi[kPaths];
+#pragma unroll
+    for (int p = 0; p < kPaths; ++p) {
+      const long long n = base + p * T;
+      prefix[p] = 0.0;
+      basket[p] = 0.0;
+      lo[p] = (uint32_t)n;
+      hi[p] = (uint32_t)((uint64_t)n >> 32);
+    }
+    for (int j = 0; 2 * j < d; ++j) {
+      const double c0 = c_Lc[2 * j], d0 = c_Ld[2 * j], c1 = c_Lc[2 * j + 1], d1 = c_Ld[2 * j + 1];
+      const bool two = 2 * j + 1 < d;
+#pragma unroll
+      for (int p = 0; p < kPaths; ++p) {
+        uint32_t x[4];
+        philox4x32_10(key, lo[p], hi[p], (uint32_t)j, PCF_STREAM_BASKET, x);
+        double z0, z1;
+        box_muller_pair(x, tv, hc, z0, z1);
+        const double b0 = fma(d0, z0, prefix[p]);
+        prefix[p] = fma(c0, z0, prefix[p]);
+        basket[p] = fma(wS0, exp_table(fma(sigma, b0, drift), tv), basket[p]);  // mc_eur_multi.cpp:30
+        if (two) {
+          const double b1 = fma(d1, z1, prefix[p]);
+          prefix[p] = fma(c1, z1, prefix[p]);
+          basket[p] = fma(wS0, exp_table(fma(sigma, b1, drift), tv), basket[p]);
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kPaths; ++p) {
+      if (base + p * T < a.n1) {
+        const double v = payoff(basket[p], a.E, a.cp);
+        s1.add(v);
+        s2.add(v * v);
+      }
+    }
+  }
+  Comp v[2] = {s1, s2};
+  grid_reduce<2>(v, smem, partials, ticket, out, &link);
+}
+
 template <int D>
 static void launch_basket(Ctx& c, const BasketArgs& a, int grid, bool replay, const PeerLink& link) {
   if (replay)
@@ -326,8 +406,29 @@ int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-m
   a.wS0 = (1.0 / (double)d) * p.S0;
   a.n0 = paths.begin; a.n1 = paths.end;
   a.seed = p.seed; a.Z = d_replay;
-  int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
   const bool rp = d_replay != nullptr;
+  // constant columns below the diagonal (bitwise)? -> equicorrelation fast path
+  bool equi = !rp && !getenv("PCF_BASKET_GENERAL");
+  for (int k = 0; k < d && equi; ++k)
+    for (int i = k + 2; i < d; ++i)
+      if (L_host[i * d + k] != L_host[(k + 1) * d + k]) { equi = false; break; }
+  if (equi) {
+    double Lc[PCF_MAX_ASSETS] = {0}, Ld[PCF_MAX_ASSETS] = {0};
+    for (int k = 0; k < d; ++k) {
+      Ld[k] = L_host[k * d + k];
+      Lc[k] = (k + 1 < d) ? L_host[(k + 1) * d + k] : 0.0;
+    }
+    PCF_CUDA(cudaMemcpyToSymbolAsync(c_Lc, Lc, sizeof(Lc), 0, cudaMemcpyHostToDevice, c.stream));
+    PCF_CUDA(cudaMemcpyToSymbolAsync(c_Ld, Ld, sizeof(Ld), 0, cudaMemcpyHostToDevice, c.stream));
+    constexpr int kP = 4;
+    int grid = grid_for(c, (paths.size() + kP - 1) / kP, kBlock, 1);
+    mc_basket_equi_kernel<kP><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials,
+                                                                         c.d_ticket, c.d_out);
+    c.launches++;
+    PCF_CUDA(cudaGetLastError());
+    return PCF_OK;
+  }
+  int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
   if (d <= 2) launch_basket<2>(c, a, grid, rp, link);
   else if (d <= 4) launch_basket<4>(c, a, grid, rp, link);
   else if (d <= 8) launch_basket<8>(c, a, grid, rp, link);

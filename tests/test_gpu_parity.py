@@ -82,7 +82,8 @@ def test_mc_amer_replay_golden(gpu, golden):
         w = oracle.normals_mt19937(c["seed"], math.sqrt(T / c["M"]), c["N"] // 2 * c["M"])
         g = gpu.mc_amer(S0, E, r, sigma, T, c["N"], c["M"], c["payoff"], replay=w)
         assert rel(g.price, c["price"]) < REPLAY_TOL, c
-        assert g.launches == 2 + 2 * (c["M"] - 1)  # paths + (moments, decide) per date + final
+        # paths [+ pad] + one fused sweep kernel per date (M of them when M >= 2) + final
+        assert g.launches == 2 + (c["M"] if c["M"] >= 2 else 0) + (1 if c["N"] % 4 else 0)
 
 
 def test_mc_amer_few_itm_branches(gpu):
@@ -101,6 +102,17 @@ def test_basket_replay_vs_oracle(gpu):
         o = oracle.mc_basket(100, 100, .05, .2, 1, N, pf, d, rho, Z)
         g = gpu.mc_eur_multi(100, 100, .05, .2, 1, N, pf, d, rho, replay=Z)
         assert rel(g.price, o) < REPLAY_TOL, (d, rho)
+
+
+def test_basket_equicorrelation_fast_path_is_bit_identical(gpu, monkeypatch):
+    # the constant-column shortcut performs the same chain of FMAs as the general triangular product
+    for d, rho, N in [(16, 0.5, 300_001), (5, -0.1, 100_000), (32, 0.3, 50_000), (1, 0.0, 10_000), (2, 0.9, 10_001)]:
+        monkeypatch.delenv("PCF_BASKET_GENERAL", raising=False)
+        fast = gpu.mc_eur_multi(*P1, N, "call", d, rho, seed=77)
+        monkeypatch.setenv("PCF_BASKET_GENERAL", "1")
+        gen = gpu.mc_eur_multi(*P1, N, "call", d, rho, seed=77)
+        monkeypatch.delenv("PCF_BASKET_GENERAL", raising=False)
+        assert rel(fast.sum, gen.sum) < 1e-14 and rel(fast.sumsq, gen.sumsq) < 1e-14, (d, rho)
 
 
 def test_basket_cholesky_matches_oracle(gpu):
