@@ -19,6 +19,7 @@
 #include <thread>
 #include <vector>
 #include "common.cuh"
+#include "binom_math.cuh"
 
 namespace pcf {
 
@@ -31,7 +32,6 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
                 PeerLink* final_link);
 size_t amer_workspace_bytes(long long local_pairs, int M);
 int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid, const PeerLink& link);
-void binom_lattice(double r, double sigma, double T, long long N, double& u, double& d, double& p, double& q);
 int run_philox_kat(Ctx& c, const unsigned int ctr[4], const unsigned int key[2], uint32_t* d_out);
 int run_normal_stream(Ctx& c, uint64_t seed, uint32_t stream, uint64_t index0, long long count, int T,
                       double scale, double* d_out);
