@@ -6,7 +6,7 @@
 //   paths  double[M][Nl]   row m-1 holds S at date m (row 0 of the reference, S0, is never read by the
 //                          sweep and is not stored). Pair p owns columns p and p + Nl/2, exactly the
 //                          reference's antithetic halves; both stores of a warp are 256 B contiguous.
-//   when   int32[Nl]       exercise date; bit 30 set when the cash flow was booked by the regression
+//   when   int32[Np]       exercise date; bit 30 set when the cash flow was booked by the regression
 //                          branch (mc_amer.cpp:100-103), which books payoff(S - E, E) [SURVEY F1]
 //   cash   double[Nl]      TRUE payoff at paths[when][n] -- the value the reference re-gathers at
 //                          mc_amer.cpp:50; carrying it turns that row gather into a coalesced read.
@@ -29,6 +29,8 @@
 namespace pcf {
 
 constexpr int kAmerBlock = 256;
+typedef int when_t;  // exercise date + flag. (uint16 was tried: 10% fewer bytes but 8% SLOWER sweeps -- 8-byte
+                     // quarter-sector state stores; profiles/r1_notes.md)
 constexpr int kQuirkBit = 1 << 30;
 constexpr int kMaxDates = 2048;  // discount tables: constant memory -> staged into shared memory per block
 
@@ -69,7 +71,7 @@ __device__ __forceinline__ void amer_step(double& Sp, double& Sm, double z, cons
 template <bool kReplay, bool kSmallExp>
 __global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, const MathTables* __restrict__ tables,
                                                                 double* __restrict__ paths,
-                                                                int* __restrict__ when,
+                                                                when_t* __restrict__ when,
                                                                 double* __restrict__ cash) {
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
@@ -102,15 +104,15 @@ __global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, cons
       }
     }
     // mc_amer.cpp:23-27: exercise_when = M, exercise_st = payoff(S_M)
-    when[p] = a.M;
-    when[p + a.H] = a.M;
+    when[p] = (when_t)a.M;
+    when[p + a.H] = (when_t)a.M;
     cash[p] = payoff(Sp, a.E, a.cp);
     cash[p + a.H] = payoff(Sm, a.E, a.cp);
   }
 }
 
 // Padding columns [2H, Np): S chosen so that payoff == 0 at every date, state = (M, 0).
-__global__ void amer_pad_kernel(double* __restrict__ paths, int* __restrict__ when, double* __restrict__ cash,
+__global__ void amer_pad_kernel(double* __restrict__ paths, when_t* __restrict__ when, double* __restrict__ cash,
                                 long long Nl, long long Np, int M, int cp) {
   const long long pad = Np - Nl;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pad * (M + 1);
@@ -119,7 +121,7 @@ __global__ void amer_pad_kernel(double* __restrict__ paths, int* __restrict__ wh
     if (row < M) {
       paths[row * Np + col] = cp > 0 ? 0.0 : 1e300;  // call: S - E < 0;  put: E - S < 0
     } else {
-      when[col] = M;
+      when[col] = (when_t)M;
       cash[col] = 0.0;
     }
   }
@@ -158,6 +160,9 @@ __device__ bool solve3_reference_order(const double* mom, double coef[3]) {
 // out[0..7] = n_itm, Sx, Sx^2, Sx^3, Sx^4, Sy, Syx, Syx^2 with x = S - E, y = discounted cash flow; products
 // are formed exactly like the reference forms them (left to right, no FMA): only the summation order differs.
 constexpr int kMomFold = 4;
+constexpr int kSweepUnroll = 2;
+constexpr int kSweepBlock = 128;
+constexpr int kSweepBlocksPerSM = 3;
 
 __device__ __forceinline__ void amer_decide_one(double S, int& wq, double& cs, bool& changed, int mode, double c0,
                                                 double c1, double c2, double E, int cp, int m,
@@ -204,8 +209,8 @@ __device__ __forceinline__ void amer_moment_terms(double S, int wq, double cs, d
 }
 
 template <bool kDecide, bool kMoments>
-__global__ void __launch_bounds__(kAmerBlock, 2) amer_sweep_kernel(
-    const double* __restrict__ S_m, const double* __restrict__ S_prev, int* __restrict__ when,
+__global__ void __launch_bounds__(kSweepBlock, kSweepBlocksPerSM) amer_sweep_kernel(
+    const double* __restrict__ S_m, const double* __restrict__ S_prev, when_t* __restrict__ when,
     double* __restrict__ cash, long long Np, double E, int cp, int m, int M,
     const double* __restrict__ mom_in, PeerLink link_in, PeerLink link_out, double* partials,
     unsigned int* ticket, double* mom_out, int* err_flag) {
@@ -256,45 +261,62 @@ __global__ void __launch_bounds__(kAmerBlock, 2) amer_sweep_kernel(
   const double2* Sp2 = reinterpret_cast<const double2*>(S_prev);
   int4* W4 = reinterpret_cast<int4*>(when);
   double2* C2 = reinterpret_cast<double2*>(cash);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads;
-       i += (long long)gridDim.x * blockDim.x) {
-    // 7 independent 16-byte loads per thread: one 32-byte sector of each row, the state of 4 paths
-    double2 sa = make_double2(0, 0), sb = sa, pa = sa, pb = sa;
-    if (kDecide) {
-      sa = __ldcs(Sm2 + 2 * i);
-      sb = __ldcs(Sm2 + 2 * i + 1);
-    }
-    if (kMoments) {
-      pa = __ldcs(Sp2 + 2 * i);
-      pb = __ldcs(Sp2 + 2 * i + 1);
-    }
-    int4 w = W4[i];
-    double2 ca = C2[2 * i], cb = C2[2 * i + 1];
-    if (kDecide && mode != 0) {
-      bool changed = false;
-      amer_decide_one(sa.x, w.x, ca.x, changed, mode, c0, c1, c2, E, cp, m, s_disc);
-      amer_decide_one(sa.y, w.y, ca.y, changed, mode, c0, c1, c2, E, cp, m, s_disc);
-      amer_decide_one(sb.x, w.z, cb.x, changed, mode, c0, c1, c2, E, cp, m, s_disc);
-      amer_decide_one(sb.y, w.w, cb.y, changed, mode, c0, c1, c2, E, cp, m, s_disc);
-      if (changed) {  // whole sectors back: no partial-sector fill from DRAM
-        W4[i] = w;
-        C2[2 * i] = ca;
-        C2[2 * i + 1] = cb;
-      }
-    }
-    if (kMoments) {
-      amer_moment_terms(pa.x, w.x, ca.x, E, cp, m - 1, s_disc, run);
-      amer_moment_terms(pa.y, w.y, ca.y, E, cp, m - 1, s_disc, run);
-      amer_moment_terms(pb.x, w.z, cb.x, E, cp, m - 1, s_disc, run);
-      amer_moment_terms(pb.y, w.w, cb.y, E, cp, m - 1, s_disc, run);
-      if (++fold == kMomFold) {
+  const long long T = (long long)gridDim.x * blockDim.x;
+  // kSweepUnroll quads (of 4 paths = one 32-byte sector per array) per thread iteration: all 7 x kSweepUnroll
+  // 16-byte loads are issued before the first use, which keeps ~200 B per thread in flight -- the kernel is
+  // DRAM-latency bound otherwise (ncu: long_scoreboard).
+  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < quads; base += T * kSweepUnroll) {
+    double2 sa[kSweepUnroll], sb[kSweepUnroll], pa[kSweepUnroll], pb[kSweepUnroll], ca[kSweepUnroll], cb[kSweepUnroll];
+    int4 w[kSweepUnroll];  // unpacked dates
+    bool live[kSweepUnroll];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          acc[k].add(run[k]);
-          run[k] = 0.0;
-        }
-        fold = 0;
+    for (int u = 0; u < kSweepUnroll; ++u) {
+      const long long i = base + u * T;
+      live[u] = i < quads;
+      const long long j = live[u] ? i : base;  // clamp: loads stay in bounds, results are discarded
+      sa[u] = sb[u] = pa[u] = pb[u] = make_double2(0, 0);
+      if (kDecide) {
+        sa[u] = __ldcs(Sm2 + 2 * j);
+        sb[u] = __ldcs(Sm2 + 2 * j + 1);
       }
+      if (kMoments) {
+        pa[u] = __ldcs(Sp2 + 2 * j);
+        pb[u] = __ldcs(Sp2 + 2 * j + 1);
+      }
+      w[u] = W4[j];
+      ca[u] = C2[2 * j];
+      cb[u] = C2[2 * j + 1];
+    }
+#pragma unroll
+    for (int u = 0; u < kSweepUnroll; ++u) {
+      if (!live[u]) continue;
+      const long long i = base + u * T;
+      if (kDecide && mode != 0) {
+        bool changed = false;
+        amer_decide_one(sa[u].x, w[u].x, ca[u].x, changed, mode, c0, c1, c2, E, cp, m, s_disc);
+        amer_decide_one(sa[u].y, w[u].y, ca[u].y, changed, mode, c0, c1, c2, E, cp, m, s_disc);
+        amer_decide_one(sb[u].x, w[u].z, cb[u].x, changed, mode, c0, c1, c2, E, cp, m, s_disc);
+        amer_decide_one(sb[u].y, w[u].w, cb[u].y, changed, mode, c0, c1, c2, E, cp, m, s_disc);
+        if (changed) {  // whole sectors back: no partial-sector fill from DRAM
+          W4[i] = w[u];
+          C2[2 * i] = ca[u];
+          C2[2 * i + 1] = cb[u];
+        }
+      }
+      if (kMoments) {
+        amer_moment_terms(pa[u].x, w[u].x, ca[u].x, E, cp, m - 1, s_disc, run);
+        amer_moment_terms(pa[u].y, w[u].y, ca[u].y, E, cp, m - 1, s_disc, run);
+        amer_moment_terms(pb[u].x, w[u].z, cb[u].x, E, cp, m - 1, s_disc, run);
+        amer_moment_terms(pb[u].y, w[u].w, cb[u].y, E, cp, m - 1, s_disc, run);
+      }
+    }
+    if (kMoments && ++fold == kMomFold) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[k].add(run[k]);
+        run[k] = 0.0;
+      }
+      fold = 0;
     }
   }
   if (kMoments) {
@@ -305,7 +327,7 @@ __global__ void __launch_bounds__(kAmerBlock, 2) amer_sweep_kernel(
 }
 
 // mc_amer.cpp:109-111: sum of discounted booked cash flows (+ sum of squares for the error bar).
-__global__ void __launch_bounds__(kAmerBlock) amer_final_kernel(const int* __restrict__ when,
+__global__ void __launch_bounds__(kAmerBlock) amer_final_kernel(const when_t* __restrict__ when,
                                                                 const double* __restrict__ cash,
                                                                 long long Nl, double E, int cp, int M,
                                                                 PeerLink link, double* partials,
@@ -352,7 +374,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   char* base = (char*)c.workspace + ws_offset;
   double* paths = (double*)base;
   double* cash = paths + (size_t)M * Np;
-  int* when = (int*)(cash + Np);
+  when_t* when = (when_t*)(cash + Np);
 
   AmerArgs a;
   a.S0 = p.S0; a.E = p.E; a.cp = p.cp; a.M = M;
@@ -379,7 +401,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   // Backward sweep m = M-1 .. 1 (mc_amer.cpp:31). Kernel for date m consumes the moments of date m and produces
   // those of date m-1. Peer path: moments travel through the NVLink mailboxes (publish in the producing kernel,
   // gather in the consuming one); NCCL path: an all-reduce of the 8 doubles between two kernels.
-  int grid = grid_for(c, Np / 4, kAmerBlock, 2);
+  int grid = grid_for(c, (Np / 4 + kSweepUnroll - 1) / kSweepUnroll, kSweepBlock, kSweepBlocksPerSM);
   const size_t dsm = sizeof(double) * (M + 1);
   double* mom[2] = {c.d_out + 8, c.d_out + 16};
   auto row = [&](int m) { return paths + (size_t)(m - 1) * Np; };
@@ -387,7 +409,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   none.world = 1;
   if (M >= 2) {
     PeerLink l_out = next_link(c);
-    amer_sweep_kernel<false, true><<<grid, kAmerBlock, dsm, c.stream>>>(
+    amer_sweep_kernel<false, true><<<grid, kSweepBlock, dsm, c.stream>>>(
         nullptr, row(M - 1), when, cash, Np, p.E, p.cp, M, M, nullptr, none, l_out, c.d_partials, c.d_ticket,
         mom[(M - 1) & 1], c.d_flag);
     c.launches++;
@@ -396,11 +418,11 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
       if (!use_peer(c)) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));
       if (m > 1) {
         l_out = next_link(c);
-        amer_sweep_kernel<true, true><<<grid, kAmerBlock, dsm, c.stream>>>(
+        amer_sweep_kernel<true, true><<<grid, kSweepBlock, dsm, c.stream>>>(
             row(m), row(m - 1), when, cash, Np, p.E, p.cp, m, M, mom[m & 1], l_in, l_out, c.d_partials,
             c.d_ticket, mom[(m - 1) & 1], c.d_flag);
       } else {
-        amer_sweep_kernel<true, false><<<grid, kAmerBlock, dsm, c.stream>>>(
+        amer_sweep_kernel<true, false><<<grid, kSweepBlock, dsm, c.stream>>>(
             row(1), nullptr, when, cash, Np, p.E, p.cp, 1, M, mom[1], l_in, none, c.d_partials, c.d_ticket,
             nullptr, c.d_flag);
       }

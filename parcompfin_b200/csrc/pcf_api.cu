@@ -282,6 +282,7 @@ extern "C" {
 
 int pcf_init(int gpus) {
   if (!g_ctx.empty()) return PCF_OK;
+  setenv("CUDA_MODULE_LOADING", "EAGER", 0);  // kernel images load with the context (T_overall), not inside the first pricing call
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -341,6 +342,7 @@ int pcf_nccl_unique_id(unsigned char id[128]) {
 int pcf_init_rank(int rank, int world, int device, const unsigned char* nccl_id) {
   if (!g_ctx.empty()) return PCF_OK;
   if (world < 1 || rank < 0 || rank >= world) return PCF_EINVAL;
+  setenv("CUDA_MODULE_LOADING", "EAGER", 0);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
