@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "reduce.cuh"
 #include "rng.cuh"
+#include <cstdlib>
 
 namespace pcf {
 
@@ -41,7 +42,6 @@ struct AmerArgs {
   double S0, E;
   double adt;   // (r - sigma^2/2) dt
   double cs;    // sigma*sd (native) | sigma (replay)
-  double exp_adt;  // e^{adt} (host, glibc)
   int cp, M;
   long long p0;       // first global pair of this GPU
   long long H;        // local pairs; Nl = 2H
@@ -50,64 +50,104 @@ struct AmerArgs {
   const double* w;    // replay: w[(p-p0)*M + (m-1)]
 };
 
-// a6: one thread per antithetic pair, S+ and S- in registers, one Philox block per two dates.
-// exp((r-s^2/2)dt +- s w) = e^{a} e^{+-x}: with |x| small (kSmallExp) both factors come from one even/odd
-// Taylor split (13 FP64 for the pair); otherwise two table-driven exponentials.
-template <bool kSmallExp>
-__device__ __forceinline__ void amer_step(double& Sp, double& Sm, double z, const AmerArgs& a, double ea,
-                                          const TableView& tv, const Hoisted& hc) {
-  const double sw = a.cs * z;
-  if (kSmallExp) {
-    double ep, em;
-    exp_small_pm(sw, hc, ep, em);
-    Sp *= ea * ep;  // common.h:202
-    Sm *= ea * em;  // common.h:203
-  } else {
-    Sp *= exp_table(a.adt + sw, tv);
-    Sm *= exp_table(a.adt - sw, tv);
-  }
+// a6: antithetic pairs, S+ and S- in registers, one Philox block per two dates, kPairs pairs per thread.
+// exp((r-s^2/2)dt +- s w): x = s w is reduced once, x = (32k + j) ln2/32 + r, and
+//   e^{a+x} = 2^k  [e^a 2^{ j/32}] (C(r) + S(r)),   e^{a-x} = 2^-k [e^a 2^{-j/32}] (C(r) - S(r))
+// with C/S the even/odd parts of e^r (degree 6/5; |r| <= ln2/64). The bracketed factors come from a per-call
+// 32-entry table (c_amer_T, e^a folded in on the host), one LDS.128 per step: 15 FP64 for both exponentials.
+__constant__ double c_amer_T[2 * kExpEntries];  // (e^a 2^(j/32), e^a 2^(-j/32)), j = 0..31
+
+__device__ __forceinline__ void amer_step(double& Sp, double& Sm, double z, double cs, const Pair* __restrict__ s_T) {
+  const double x = cs * z;
+  const double magic = 6755399441055744.0;
+  const double t = fma(x, 46.16624130844683, magic);
+  const double kf = t - magic;
+  double r = fma(kf, -0.02166084939249829, x);
+  r = fma(kf, -7.247021293269686e-19, r);
+  const uint32_t n = (uint32_t)__double2loint(t);
+  const Pair T = s_T[(n & 31u) * kRep16];
+  const double r2 = r * r;
+  double ce = fma(r2, 1.0 / 720.0, 1.0 / 24.0);
+  ce = fma(ce, r2, 0.5);
+  ce = fma(ce, r2, 1.0);
+  double so = fma(r2, 1.0 / 120.0, 1.0 / 6.0);
+  so = fma(so, r2, 1.0);
+  so *= r;
+  const double ep = T.x * (ce + so), em = T.y * (ce - so);
+  const int k = (int)n >> 5;
+  // scale by 2^(+-k) through the exponent field (|k| is small: |x| = sigma sqrt(dt) |z|)
+  const double fp = __hiloint2double(__double2hiint(ep) + (k << 20), __double2loint(ep));
+  const double fm = __hiloint2double(__double2hiint(em) - (k << 20), __double2loint(em));
+  Sp *= fp;  // common.h:202
+  Sm *= fm;  // common.h:203
 }
 
-template <bool kReplay, bool kSmallExp>
-__global__ void __launch_bounds__(kAmerBlock) amer_paths_kernel(AmerArgs a, const MathTables* __restrict__ tables,
-                                                                double* __restrict__ paths,
-                                                                when_t* __restrict__ when,
-                                                                double* __restrict__ cash) {
+template <bool kReplay, int kPairs, int kMinBlocks>
+__global__ void __launch_bounds__(kAmerBlock, kMinBlocks) amer_paths_kernel(AmerArgs a, const MathTables* __restrict__ tables,
+                                                                   double* __restrict__ paths,
+                                                                   when_t* __restrict__ when,
+                                                                   double* __restrict__ cash) {
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
+  Pair* s_T = reinterpret_cast<Pair*>(tab_smem + kTableSmemBytes);
+  for (int i = threadIdx.x; i < kExpEntries * kRep16; i += blockDim.x) {
+    s_T[i].x = c_amer_T[2 * (i / kRep16)];
+    s_T[i].y = c_amer_T[2 * (i / kRep16) + 1];
+  }
+  __syncthreads();
+  const Pair* my_T = s_T + (threadIdx.x & (kRep16 - 1));
   Hoisted hc;
   hc.load();
   const PhiloxKey key(a.seed);
-  const long long Nl = a.Np;  // row stride
-  const double ea = a.exp_adt;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.H;
-       p += (long long)gridDim.x * blockDim.x) {
-    double Sp = a.S0, Sm = a.S0;
+  const long long Np = a.Np;  // row stride
+  const long long T = (long long)gridDim.x * blockDim.x;
+  const double cs = a.cs;
+  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < a.H; base += T * kPairs) {
+    double Sp[kPairs], Sm[kPairs];
+    long long pp[kPairs];
+#pragma unroll
+    for (int q = 0; q < kPairs; ++q) {
+      Sp[q] = a.S0;
+      Sm[q] = a.S0;
+      pp[q] = (base + q * T < a.H) ? base + q * T : base;  // clamp: duplicates rewrite identical values
+    }
     if (kReplay) {
       for (int m = 1; m <= a.M; ++m) {
-        amer_step<kSmallExp>(Sp, Sm, a.w[p * (long long)a.M + (m - 1)], a, ea, tv, hc);
-        __stcs(paths + (size_t)(m - 1) * Nl + p, Sp);
-        __stcs(paths + (size_t)(m - 1) * Nl + p + a.H, Sm);
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+          amer_step(Sp[q], Sm[q], a.w[pp[q] * (long long)a.M + (m - 1)], cs, my_T);
+          __stcs(paths + (size_t)(m - 1) * Np + pp[q], Sp[q]);
+          __stcs(paths + (size_t)(m - 1) * Np + pp[q] + a.H, Sm[q]);
+        }
       }
     } else {
       for (int m = 1; m <= a.M; m += 2) {
-        double z0, z1;
-        normal_pair(key, (uint64_t)(a.p0 + p), (uint32_t)((m - 1) >> 1), PCF_STREAM_AMER, tv, hc, z0, z1);
-        amer_step<kSmallExp>(Sp, Sm, z0, a, ea, tv, hc);
-        __stcs(paths + (size_t)(m - 1) * Nl + p, Sp);
-        __stcs(paths + (size_t)(m - 1) * Nl + p + a.H, Sm);
-        if (m + 1 <= a.M) {
-          amer_step<kSmallExp>(Sp, Sm, z1, a, ea, tv, hc);
-          __stcs(paths + (size_t)m * Nl + p, Sp);
-          __stcs(paths + (size_t)m * Nl + p + a.H, Sm);
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+          const uint64_t g = (uint64_t)(a.p0 + pp[q]);
+          uint32_t x[4];
+          philox4x32_10(key, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)((m - 1) >> 1), PCF_STREAM_AMER, x);
+          double z0, z1;
+          box_muller_pair(x, tv, hc, z0, z1);
+          amer_step(Sp[q], Sm[q], z0, cs, my_T);
+          __stcs(paths + (size_t)(m - 1) * Np + pp[q], Sp[q]);
+          __stcs(paths + (size_t)(m - 1) * Np + pp[q] + a.H, Sm[q]);
+          if (m + 1 <= a.M) {
+            amer_step(Sp[q], Sm[q], z1, cs, my_T);
+            __stcs(paths + (size_t)m * Np + pp[q], Sp[q]);
+            __stcs(paths + (size_t)m * Np + pp[q] + a.H, Sm[q]);
+          }
         }
       }
     }
     // mc_amer.cpp:23-27: exercise_when = M, exercise_st = payoff(S_M)
-    when[p] = (when_t)a.M;
-    when[p + a.H] = (when_t)a.M;
-    cash[p] = payoff(Sp, a.E, a.cp);
-    cash[p + a.H] = payoff(Sm, a.E, a.cp);
+#pragma unroll
+    for (int q = 0; q < kPairs; ++q) {
+      when[pp[q]] = (when_t)a.M;
+      when[pp[q] + a.H] = (when_t)a.M;
+      cash[pp[q]] = payoff(Sp[q], a.E, a.cp);
+      cash[pp[q] + a.H] = payoff(Sm[q], a.E, a.cp);
+    }
   }
 }
 
@@ -382,15 +422,43 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   a.cs = d_replay ? p.sigma : p.sigma * sqrt(dt);
   a.p0 = pairs.begin; a.H = H; a.Np = Np; a.seed = p.seed; a.w = d_replay;
 
-  a.exp_adt = exp(a.adt);
-  const bool small = fabs(a.cs) * kZMax <= kSmallExpBound;
-  int grid_gen = grid_for(c, H, kAmerBlock, 4);
-  if (d_replay)
-    amer_paths_kernel<true, false><<<grid_gen, kAmerBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, paths, when, cash);
-  else if (small)
-    amer_paths_kernel<false, true><<<grid_gen, kAmerBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, paths, when, cash);
-  else
-    amer_paths_kernel<false, false><<<grid_gen, kAmerBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, paths, when, cash);
+  {
+    // per-call table: e^a 2^(+-j/32), a = (r - sigma^2/2) dt, in long double then rounded once
+    double Tt[2 * kExpEntries];
+    const long double ea = expl((long double)a.adt);
+    for (int j = 0; j < kExpEntries; ++j) {
+      Tt[2 * j] = (double)(ea * exp2l((long double)j / kExpEntries));
+      Tt[2 * j + 1] = (double)(ea * exp2l(-(long double)j / kExpEntries));
+    }
+    PCF_CUDA(cudaMemcpyToSymbolAsync(c_amer_T, Tt, sizeof(Tt), 0, cudaMemcpyHostToDevice, c.stream));
+  }
+  const size_t gen_smem = kTableSmemBytes + (size_t)kExpEntries * kRep16 * sizeof(Pair);
+  if (d_replay) {
+    int grid_gen = grid_for(c, H, kAmerBlock, 2);
+    amer_paths_kernel<true, 1, 2><<<grid_gen, kAmerBlock, gen_smem, c.stream>>>(a, c.d_tables, paths, when, cash);
+  } else {
+    // launch shape: PCF_AMER_GEN = <pairs per thread><CTAs per SM> (tuning knob)
+    const char* v = getenv("PCF_AMER_GEN");
+    const int variant = v ? atoi(v) : 22;
+#define PCF_GEN_CASE(P, B)                                                                                    \
+  case P * 10 + B: {                                                                                          \
+    int grid_gen = grid_for(c, (H + P - 1) / P, kAmerBlock, B);                                               \
+    amer_paths_kernel<false, P, B><<<grid_gen, kAmerBlock, gen_smem, c.stream>>>(a, c.d_tables, paths, when, cash); \
+  } break;
+    switch (variant) {
+      PCF_GEN_CASE(1, 4)
+      PCF_GEN_CASE(2, 2)
+      PCF_GEN_CASE(2, 3)
+      PCF_GEN_CASE(3, 2)
+      PCF_GEN_CASE(4, 1)
+      PCF_GEN_CASE(4, 2)
+      PCF_GEN_CASE(6, 1)
+      default:
+        set_last_error("unknown PCF_AMER_GEN");
+        return PCF_EINVAL;
+    }
+#undef PCF_GEN_CASE
+  }
   c.launches++;
   if (Np != Nl) {
     amer_pad_kernel<<<1, 128, 0, c.stream>>>(paths, when, cash, Nl, Np, M, p.cp);

@@ -25,8 +25,8 @@ struct EurArgs {
 
 // kPairs Philox blocks (2*kPairs paths) per thread iteration: independent integer and FP64 instruction streams
 // in one loop body (see mc_asia_kernel); sums are folded into the compensated totals once per iteration.
-template <bool kReplay, bool kSmallExp, int kPairs>
-__global__ void __launch_bounds__(kBlock, 1) mc_eur_kernel(EurArgs a, const MathTables* __restrict__ tables, PeerLink link,
+template <bool kReplay, bool kSmallExp, int kPairs, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) mc_eur_kernel(EurArgs a, const MathTables* __restrict__ tables, PeerLink link,
                                                            double* partials, unsigned int* ticket, double* out) {
   __shared__ double smem[2 * 2 * 32];
   extern __shared__ __align__(16) unsigned char tab_smem[];
@@ -72,17 +72,34 @@ int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay,
   a.sqrtT = sqrt(p.T);
   a.k0 = pairs.begin; a.k1 = pairs.end;
   a.seed = p.seed; a.w = d_replay;
-  constexpr int kP = 4;
   const bool small = fabs(a.drift) + fabs(a.sigma * a.sqrtT) * kZMax <= kSmallExpBound;
   if (d_replay) {
     int grid = grid_for(c, pairs.size(), kBlock, 2);
-    mc_eur_kernel<true, false, 1><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+    mc_eur_kernel<true, false, 1, 2><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
   } else {
-    int grid = grid_for(c, (pairs.size() + kP - 1) / kP, kBlock, 1);
-    if (small)
-      mc_eur_kernel<false, true, kP><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
-    else
-      mc_eur_kernel<false, false, kP><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+    const char* v = getenv("PCF_EUR_VARIANT");  // <pairs per thread><CTAs per SM> (tuning knob)
+    const int variant = v ? atoi(v) : 81;
+#define PCF_EUR_CASE(P, B)                                                                                        \
+  case P * 10 + B: {                                                                                              \
+    int grid = grid_for(c, (pairs.size() + P - 1) / P, kBlock, B);                                                \
+    if (small)                                                                                                    \
+      mc_eur_kernel<false, true, P, B><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out); \
+    else                                                                                                          \
+      mc_eur_kernel<false, false, P, B><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out); \
+  } break;
+    switch (variant) {
+      PCF_EUR_CASE(1, 4)
+      PCF_EUR_CASE(2, 2)
+      PCF_EUR_CASE(2, 3)
+      PCF_EUR_CASE(3, 2)
+      PCF_EUR_CASE(4, 1)
+      PCF_EUR_CASE(6, 1)
+      PCF_EUR_CASE(8, 1)
+      default:
+        set_last_error("unknown PCF_EUR_VARIANT");
+        return PCF_EINVAL;
+    }
+#undef PCF_EUR_CASE
   }
   c.launches++;
   PCF_CUDA(cudaGetLastError());
@@ -328,8 +345,8 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const M
 __constant__ double c_Lc[PCF_MAX_ASSETS];  // c_k  = L[k+1][k]
 __constant__ double c_Ld[PCF_MAX_ASSETS];  // d_a  = L[a][a]
 
-template <int kPaths>
-__global__ void __launch_bounds__(kBlock, 1) mc_basket_equi_kernel(BasketArgs a, const MathTables* __restrict__ tables,
+template <int kPaths, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) mc_basket_equi_kernel(BasketArgs a, const MathTables* __restrict__ tables,
                                                                    PeerLink link, double* partials,
                                                                    unsigned int* ticket, double* out) {
   __shared__ double smem[2 * 2 * 32];
@@ -420,10 +437,28 @@ int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-m
     }
     PCF_CUDA(cudaMemcpyToSymbolAsync(c_Lc, Lc, sizeof(Lc), 0, cudaMemcpyHostToDevice, c.stream));
     PCF_CUDA(cudaMemcpyToSymbolAsync(c_Ld, Ld, sizeof(Ld), 0, cudaMemcpyHostToDevice, c.stream));
-    constexpr int kP = 4;
-    int grid = grid_for(c, (paths.size() + kP - 1) / kP, kBlock, 1);
-    mc_basket_equi_kernel<kP><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials,
-                                                                         c.d_ticket, c.d_out);
+    const char* v = getenv("PCF_BASKET_VARIANT");  // <paths per thread><CTAs per SM> (tuning knob)
+    const int variant = v ? atoi(v) : 61;
+#define PCF_BASKET_CASE(P, B)                                                                              \
+  case P * 10 + B: {                                                                                       \
+    int grid = grid_for(c, (paths.size() + P - 1) / P, kBlock, B);                                         \
+    mc_basket_equi_kernel<P, B><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, \
+                                                                            c.d_ticket, c.d_out);          \
+  } break;
+    switch (variant) {
+      PCF_BASKET_CASE(1, 4)
+      PCF_BASKET_CASE(2, 2)
+      PCF_BASKET_CASE(2, 3)
+      PCF_BASKET_CASE(3, 2)
+      PCF_BASKET_CASE(4, 1)
+      PCF_BASKET_CASE(4, 2)
+      PCF_BASKET_CASE(6, 1)
+      PCF_BASKET_CASE(8, 1)
+      default:
+        set_last_error("unknown PCF_BASKET_VARIANT");
+        return PCF_EINVAL;
+    }
+#undef PCF_BASKET_CASE
     c.launches++;
     PCF_CUDA(cudaGetLastError());
     return PCF_OK;
