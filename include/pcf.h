@@ -44,6 +44,11 @@ typedef enum pcf_status {
 #define PCF_FLAG_BINOM_WINDOW 0x1u /* binom_embar: skip term pairs whose weight underflows (reported
                                       separately from the full term sum; default off)               */
 
+#define PCF_FLAG_AMER_LSM 0x2u     /* mc_amer: textbook Longstaff-Schwartz decision instead of the reference's
+                                      (SURVEY F1 / 8f.3): exercise when the TRUE payoff exceeds the fitted
+                                      continuation value and book that payoff. Off by default: parity with the
+                                      reference means reproducing its rule.                                     */
+
 /* Normal-stream ids (word 3 of the Philox counter), one per method. */
 #define PCF_STREAM_EUR 0u
 #define PCF_STREAM_ASIA 1u

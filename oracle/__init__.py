@@ -42,6 +42,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_pathsfinder.argtypes = [_d] * 4 + [_ll, _i, _P, _P]
         L.oracle_mc_amer.restype = _d
         L.oracle_mc_amer.argtypes = [_d] * 5 + [_ll, _i, _i, _P, ctypes.POINTER(_i)]
+        L.oracle_mc_amer_lsm.restype = _d
+        L.oracle_mc_amer_lsm.argtypes = [_d] * 5 + [_ll, _i, _i, _P, ctypes.POINTER(_i)]
         L.oracle_chol_equicorr.restype = _i
         L.oracle_chol_equicorr.argtypes = [_i, _d, _P]
         L.oracle_mc_basket.restype = _d
@@ -98,10 +100,11 @@ def pathsfinder(S0, r, sigma, T, N, M, w) -> np.ndarray:
     return paths
 
 
-def mc_amer(S0, E, r, sigma, T, N, M, payoff_fun, w):
+def mc_amer(S0, E, r, sigma, T, N, M, payoff_fun, w, lsm=False):
     w = np.ascontiguousarray(w, dtype=np.float64)
     st = _i()
-    price = lib().oracle_mc_amer(S0, E, r, sigma, T, N, M, _cp(payoff_fun), _p(w), ctypes.byref(st))
+    fn = lib().oracle_mc_amer_lsm if lsm else lib().oracle_mc_amer
+    price = fn(S0, E, r, sigma, T, N, M, _cp(payoff_fun), _p(w), ctypes.byref(st))
     if st.value == 1:
         raise ValueError("N needs to be divisible by 2 for finding paths")
     if st.value == 2:

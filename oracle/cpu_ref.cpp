@@ -137,8 +137,24 @@ bool solve3(const double x[3][3], const double y[3], double coef[3]) {
 //   * x == -1 is the "out of the money" sentinel (:32,:98): an ITM path with S-E == -1 is skipped
 //   * <= 2 ITM paths: compare true payoff with cont, book the true payoff (:75-83); 0: skip (:73)
 // status: 0 ok, 1 odd N, 2 determinant <= 0.
+static double mc_amer_impl(double S0, double E, double r, double sigma, double T, long long N, int M, int cp,
+                           const double* w, int* status, bool lsm);
+
 ORACLE_API double oracle_mc_amer(double S0, double E, double r, double sigma, double T, long long N,
                                  int M, int cp, const double* w, int* status) {
+  return mc_amer_impl(S0, E, r, sigma, T, N, M, cp, w, status, false);
+}
+
+// the same scheme with the textbook Longstaff-Schwartz decision (true payoff against the
+// fitted continuation value, true payoff booked, no sentinel skip) -- what depr/mc_amer/v3/mc_amer.cpp:84
+// computed before `x` was shifted. Used to check the product's PCF_FLAG_AMER_LSM mode.
+ORACLE_API double oracle_mc_amer_lsm(double S0, double E, double r, double sigma, double T, long long N,
+                                     int M, int cp, const double* w, int* status) {
+  return mc_amer_impl(S0, E, r, sigma, T, N, M, cp, w, status, true);
+}
+
+static double mc_amer_impl(double S0, double E, double r, double sigma, double T, long long N, int M, int cp,
+                           const double* w, int* status, bool lsm) {
   *status = 0;
   std::vector<double> paths((size_t)(M + 1) * (size_t)N);
   if (oracle_pathsfinder(S0, r, sigma, T, N, M, w, paths.data())) {
@@ -198,9 +214,11 @@ ORACLE_API double oracle_mc_amer(double S0, double E, double r, double sigma, do
       return NAN;
     }
     for (long long i = 0; i < N; ++i) {
-      if (x[i] != -1) {
+      const bool itm = lsm ? (payoff(paths[(size_t)m * N + i], E, cp) > 0) : (x[i] != -1);
+      if (itm) {
         double yhat = coef[0] + coef[1] * x[i] + coef[2] * (x[i] * x[i]);  // pow(x,2) :99
-        double pv = payoff(x[i], E, cp);                                   // :100 (shifted value)
+        double pv = lsm ? payoff(paths[(size_t)m * N + i], E, cp)          // textbook rule
+                        : payoff(x[i], E, cp);                             // :100 (shifted value)
         if (pv > yhat) {
           when[i] = m;
           st[i] = pv;

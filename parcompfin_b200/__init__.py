@@ -22,6 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libpcf.so")
 PCF_OK, PCF_EINVAL_PAYOFF, PCF_EODD_N, PCF_ESINGULAR, PCF_EINVAL, PCF_ENOTPD = 0, 1, 2, 3, 4, 5
 PCF_ECUDA, PCF_ENCCL, PCF_ENOINIT, PCF_ENOMEM = 10, 11, 12, 13
 PCF_FLAG_BINOM_WINDOW = 0x1
+PCF_FLAG_AMER_LSM = 0x2
 STREAM_EUR, STREAM_ASIA, STREAM_BASKET, STREAM_AMER = 0, 1, 2, 3
 MAX_ASSETS = 32
 
@@ -233,9 +234,11 @@ def mc_asia(S0, E, r, sigma, T, N, M, payoff_fun, *, seed=0, replay=None) -> Res
     return _call("pcf_mc_asia", S0, E, r, sigma, T, N, payoff_fun, M=M, seed=seed, replay=replay)
 
 
-def mc_amer(S0, E, r, sigma, T, N, M, payoff_fun, *, seed=0, replay=None) -> Result:
-    """reference src/mc_amer.cpp:5-114"""
-    return _call("pcf_mc_amer", S0, E, r, sigma, T, N, payoff_fun, M=M, seed=seed, replay=replay)
+def mc_amer(S0, E, r, sigma, T, N, M, payoff_fun, *, seed=0, replay=None, lsm=False) -> Result:
+    """reference src/mc_amer.cpp:5-114. ``lsm=True`` switches the exercise rule to textbook Longstaff-Schwartz
+    (PCF_FLAG_AMER_LSM); the default reproduces the reference's own rule."""
+    return _call("pcf_mc_amer", S0, E, r, sigma, T, N, payoff_fun, M=M, seed=seed, replay=replay,
+                 flags=PCF_FLAG_AMER_LSM if lsm else 0)
 
 
 def binom(S0, E, r, sigma, T, N, payoff_fun, *, window=False) -> Result:

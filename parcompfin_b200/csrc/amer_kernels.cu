@@ -209,13 +209,14 @@ __device__ __forceinline__ void amer_decide_one(double S, int& wq, double& cs, b
                                                 const double* s_disc) {
   const double pv = payoff(S, E, cp);
   if (!(pv > 0.0)) return;
-  if (mode == 2) {
+  if (mode == 2 || mode == 3) {
     const double x = __dadd_rn(S, -E);
-    if (x == -1.0) return;  // the reference's sentinel collision (mc_amer.cpp:32,98)
+    if (mode == 2 && x == -1.0) return;  // the reference's sentinel collision (mc_amer.cpp:32,98)
     const double yhat = __dadd_rn(__dadd_rn(c0, __dmul_rn(c1, x)), __dmul_rn(c2, __dmul_rn(x, x)));
-    const double pq = payoff(x, E, cp);  // payoff of the SHIFTED value (mc_amer.cpp:100)
+    // reference rule: payoff of the SHIFTED value (mc_amer.cpp:100); PCF_FLAG_AMER_LSM (mode 3): the true payoff
+    const double pq = (mode == 2) ? payoff(x, E, cp) : pv;
     if (pq > yhat) {
-      wq = m | kQuirkBit;
+      wq = (mode == 2) ? (m | kQuirkBit) : m;  // mode 3 books the true payoff: st == cash
       cs = pv;
       changed = true;
     }
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepBlocksPerSM) amer_sweep_ker
     const double* __restrict__ S_m, const double* __restrict__ S_prev, when_t* __restrict__ when,
     double* __restrict__ cash, long long Np, double E, int cp, int m, int M,
     const double* __restrict__ mom_in, PeerLink link_in, PeerLink link_out, double* partials,
-    unsigned int* ticket, double* mom_out, int* err_flag) {
+    unsigned int* ticket, double* mom_out, int* err_flag, int lsm) {
   __shared__ double smem[8 * 2 * 32];
   __shared__ double s_mom[kXchgVals];
   __shared__ double s_coef[3];
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepBlocksPerSM) amer_sweep_ker
       } else {
         double coef[3];
         if (solve3_reference_order(s_mom, coef)) {
-          s_mode = 2;
+          s_mode = lsm ? 3 : 2;
           s_coef[0] = coef[0]; s_coef[1] = coef[1]; s_coef[2] = coef[2];
         } else {
           s_mode = 0;
@@ -470,6 +471,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   // those of date m-1. Peer path: moments travel through the NVLink mailboxes (publish in the producing kernel,
   // gather in the consuming one); NCCL path: an all-reduce of the 8 doubles between two kernels.
   int grid = grid_for(c, (Np / 4 + kSweepUnroll - 1) / kSweepUnroll, kSweepBlock, kSweepBlocksPerSM);
+  const int lsm = (p.flags & PCF_FLAG_AMER_LSM) ? 1 : 0;
   const size_t dsm = sizeof(double) * (M + 1);
   double* mom[2] = {c.d_out + 8, c.d_out + 16};
   auto row = [&](int m) { return paths + (size_t)(m - 1) * Np; };
@@ -479,7 +481,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
     PeerLink l_out = next_link(c);
     amer_sweep_kernel<false, true><<<grid, kSweepBlock, dsm, c.stream>>>(
         nullptr, row(M - 1), when, cash, Np, p.E, p.cp, M, M, nullptr, none, l_out, c.d_partials, c.d_ticket,
-        mom[(M - 1) & 1], c.d_flag);
+        mom[(M - 1) & 1], c.d_flag, lsm);
     c.launches++;
     for (int m = M - 1; m >= 1; --m) {
       const PeerLink l_in = l_out;
@@ -488,11 +490,11 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
         l_out = next_link(c);
         amer_sweep_kernel<true, true><<<grid, kSweepBlock, dsm, c.stream>>>(
             row(m), row(m - 1), when, cash, Np, p.E, p.cp, m, M, mom[m & 1], l_in, l_out, c.d_partials,
-            c.d_ticket, mom[(m - 1) & 1], c.d_flag);
+            c.d_ticket, mom[(m - 1) & 1], c.d_flag, lsm);
       } else {
         amer_sweep_kernel<true, false><<<grid, kSweepBlock, dsm, c.stream>>>(
             row(1), nullptr, when, cash, Np, p.E, p.cp, 1, M, mom[1], l_in, none, c.d_partials, c.d_ticket,
-            nullptr, c.d_flag);
+            nullptr, c.d_flag, lsm);
       }
       c.launches++;
     }

@@ -6,6 +6,7 @@ int main(int argc, char* argv[]) {
   std::string payoff_fun = argv[1];
   pcf_params p = frontend::base_params(payoff_fun, argv);
   p.M = frontend::getArg(argv, 8);
+  if (std::getenv("PCF_AMER_LSM")) p.flags |= PCF_FLAG_AMER_LSM;  // textbook exercise rule (off by default)
   int gpus = argc > 9 ? frontend::getArg(argv, 9) : 0;
   return frontend::run("mc_amer", pcf_mc_amer, p, payoff_fun, gpus, overall, p.M, 1);
 }

@@ -95,6 +95,23 @@ def test_mc_amer_few_itm_branches(gpu):
         assert rel(g.price, o) < REPLAY_TOL or abs(g.price - o) < 1e-15
 
 
+def test_mc_amer_textbook_lsm_mode(gpu):
+    # PCF_FLAG_AMER_LSM -- true payoff against the fitted continuation value. Replay parity with
+    # the oracle's restatement of that rule, and the price lands next to the binomial tree's American put
+    # (reference bin/binom_vanilla_amer put 100 100 0.05 0.2 1 2000 -> 6.090232044; 50 exercise dates and a
+    # quadratic basis sit ~0.5 % below it), not at the reference rule's 91.9.
+    for pf, P, N, M, seed in [("put", P1, 100_000, 50, 3), ("call", (100, 110, 0.02, 0.75, 1), 50_000, 20, 4),
+                              ("put", (100, 90, 0.02, 0.75, 1), 20_002, 200, 5)]:
+        w = oracle.normals_mt19937(seed, math.sqrt(P[4] / M), N // 2 * M)
+        o = oracle.mc_amer(*P, N, M, pf, w, lsm=True)
+        g = gpu.mc_amer(*P, N, M, pf, replay=w, lsm=True)
+        assert rel(g.price, o) < REPLAY_TOL, (pf, N, M)
+    g = gpu.mc_amer(*P1, 4_000_000, 50, "put", seed=9, lsm=True)
+    assert 6.00 < g.price < 6.0903 and g.std_error < 0.01
+    d = gpu.mc_amer(*P1, 4_000_000, 50, "put", seed=9)
+    assert d.price > 90  # the default stays the reference's rule
+
+
 def test_basket_replay_vs_oracle(gpu):
     for d, rho, N, pf in [(16, 0.5, 50000, "call"), (4, 0.5, 30000, "call"), (3, 0.2, 10001, "put"), (1, 0.0, 5000, "call"),
                           (32, 0.9, 4000, "put"), (7, -0.1, 3000, "call")]:
