@@ -82,8 +82,8 @@ def test_mc_amer_replay_golden(gpu, golden):
         w = oracle.normals_mt19937(c["seed"], math.sqrt(T / c["M"]), c["N"] // 2 * c["M"])
         g = gpu.mc_amer(S0, E, r, sigma, T, c["N"], c["M"], c["payoff"], replay=w)
         assert rel(g.price, c["price"]) < REPLAY_TOL, c
-        # paths [+ pad] + one fused sweep kernel per date (M of them when M >= 2) + final
-        assert g.launches == 2 + (c["M"] if c["M"] >= 2 else 0) + (1 if c["N"] % 4 else 0)
+        # paths [+ pad] + one fused sweep kernel per date (the kernel of date 1 also forms the final sum)
+        assert g.launches == 1 + c["M"] + (1 if c["N"] % 4 else 0)
 
 
 def test_mc_amer_few_itm_branches(gpu):
@@ -93,6 +93,19 @@ def test_mc_amer_few_itm_branches(gpu):
         o = oracle.mc_amer(100, E, .05, .2, 1, N, M, "call", w)
         g = gpu.mc_amer(100, E, .05, .2, 1, N, M, "call", replay=w)
         assert rel(g.price, o) < REPLAY_TOL or abs(g.price - o) < 1e-15
+
+
+def test_mc_amer_date_width_boundary(gpu):
+    # exercise dates are stored in 1 byte up to M = 127 and in 2 bytes beyond: both sides of the switch, both rules,
+    # paths that exercise early, late and never (every one of them re-gathers paths[when][n], mc_amer.cpp:50)
+    for M in (126, 127, 128, 129, 300):
+        for pf, P in (("put", P1), ("call", (100, 110, 0.02, 0.75, 1))):
+            N = 3002
+            w = oracle.normals_mt19937(100 + M, math.sqrt(P[4] / M), N // 2 * M)
+            for lsm in (False, True):
+                o = oracle.mc_amer(*P, N, M, pf, w, lsm=lsm)
+                g = gpu.mc_amer(*P, N, M, pf, replay=w, lsm=lsm)
+                assert rel(g.price, o) < REPLAY_TOL, (M, pf, lsm)
 
 
 def test_mc_amer_textbook_lsm_mode(gpu):
