@@ -17,8 +17,8 @@
 // (one 32-byte sector, shared by neighbours with the same date). Round-1 builds carried the gathered value in a
 // `cash[n]` array instead: 16 B/path-date of extra read+write traffic, 38.8 B/path-date in total against ~18 B now.
 //
-// Rows and `when` are padded to a multiple of 4 paths (Np) with never-in-the-money dummies so that every
-// thread streams whole 32-byte sectors (4 paths) with 16-byte vector loads.
+// Rows and `when` are padded to a multiple of 16 paths (Np) with never-in-the-money dummies so that every TMA
+// bulk copy (rows and dates) is a whole number of 16-byte granules.
 //
 // Backward sweep: ONE fused kernel per exercise date. amer_sweep_kernel for date m (a) waits for the moments of
 // date m (its own, or -- multi-GPU -- every rank's, arriving in the NVLink mailbox), solves the 3x3 normal
@@ -30,6 +30,7 @@
 #include "common.cuh"
 #include "reduce.cuh"
 #include "rng.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace pcf {
@@ -50,6 +51,7 @@ struct AmerArgs {
   long long Np;       // padded row length (multiple of 4)
   unsigned long long seed;
   const double* w;    // replay: w[(p-p0)*M + (m-1)]
+  int dbg;            // PCF_AMER_DBG & 16: timing experiment, only the last row is stored (results are wrong)
 };
 
 // a6: antithetic pairs, S+ and S- in registers, one Philox block per two dates, kPairs pairs per thread.
@@ -130,12 +132,16 @@ __global__ void __launch_bounds__(kAmerBlock, kMinBlocks) amer_paths_kernel(Amer
           double z0, z1;
           box_muller_pair(x, tv, hc, z0, z1);
           amer_step(Sp[q], Sm[q], z0, cs, my_T);
-          __stcs(paths + (size_t)(m - 1) * Np + pp[q], Sp[q]);
-          __stcs(paths + (size_t)(m - 1) * Np + pp[q] + a.H, Sm[q]);
+          if (!(a.dbg & 16) || m == a.M) {
+            __stcs(paths + (size_t)(m - 1) * Np + pp[q], Sp[q]);
+            __stcs(paths + (size_t)(m - 1) * Np + pp[q] + a.H, Sm[q]);
+          }
           if (m + 1 <= a.M) {
             amer_step(Sp[q], Sm[q], z1, cs, my_T);
-            __stcs(paths + (size_t)m * Np + pp[q], Sp[q]);
-            __stcs(paths + (size_t)m * Np + pp[q] + a.H, Sm[q]);
+            if (!(a.dbg & 16) || m + 1 == a.M) {
+              __stcs(paths + (size_t)m * Np + pp[q], Sp[q]);
+              __stcs(paths + (size_t)m * Np + pp[q] + a.H, Sm[q]);
+            }
           }
         }
       }
@@ -181,296 +187,413 @@ __device__ bool solve3_reference_order(const double* mom, double coef[3]) {
 }
 
 // a7 (mc_amer.cpp:41-106), one fused kernel per date; see the file header.
-//   kMoments: accumulate the moments of date m-1 (row S_prev) after the decision of date m and publish them
+//   kMoments: accumulate the moments of date m-1 (row m-1) after the decision of date m and publish them
 //   kFinal:   date 1 -- accumulate the discounted booked cash flows and their squares (mc_amer.cpp:109-111)
-//   first:    date M -- no decision; the state is initialised to when = M (mc_amer.cpp:23-27)
+//   first:    date M -- no decision (the state was initialised to when = M, mc_amer.cpp:23-27)
 // mom_out[0..7] = n_itm, Sx, Sx^2, Sx^3, Sx^4, Sy, Syx, Syx^2 with x = S - E, y = discounted cash flow; products
 // are formed exactly like the reference forms them (left to right, no FMA): only the summation order differs.
-constexpr int kMomFold = 8;
-constexpr int kSweepMaxBlock = 256;
+//
+// Data movement: the two rows and the date array are streamed HBM -> shared memory by the TMA engine
+// (cp.async.bulk, one elected producer thread, kTilePaths paths per stage, `stages`-deep mbarrier ring), so the
+// bytes in flight per SM are set by the ring (stages x 17 KB per CTA), not by registers x resident warps; the
+// 8 consumer warps only see shared-memory latency plus the occasional gather.
+constexpr int kMomFold = 16;  // tiles (64 paths per thread) between folds of the plain running sums
+constexpr int kTilePaths = 1024;
+constexpr int kSweepConsumers = 256;                    // 4 paths of every tile per consumer thread
+constexpr int kSweepBlock = kSweepConsumers + 32;       // + the producer warp
+constexpr int kMaxStages = 6;
+constexpr int kSweepCtasPerSM = 3;
 
-// Exercise dates of one quad of paths, packed: uint8 x 4 (one 32-bit word) or uint16 x 4 (one 64-bit word).
+template <typename WT> struct WhenBits;
+template <> struct WhenBits<uint8_t> { static constexpr int kFlag = 0x80, kMask = 0x7f; };
+template <> struct WhenBits<uint16_t> { static constexpr int kFlag = 0x8000, kMask = 0x7fff; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`; streamed data is marked evict-first in L2
+// (each row is read by two consecutive kernels 800 MB apart: no reuse to protect, and the gathers do hit L2)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+struct SweepArgs {
+  const double* paths;  // row m-1 = date m, stride Np
+  void* when;
+  long long Np;         // multiple of 16
+  double E;
+  int cp, m, M;
+  int first;            // date M: no decision
+  int lsm;              // PCF_FLAG_AMER_LSM
+  int stages;
+  int dbg;              // PCF_AMER_DBG: experiments
+  const double* mom_in;
+  double* partials;
+  unsigned int* ticket;
+  double* out;          // kMoments: the 8 moments of date m-1; kFinal: sum, sumsq
+  int* err_flag;
+};
+
 template <typename WT>
-struct WhenQuad;
-template <>
-struct WhenQuad<uint8_t> {
+__global__ void amer_fill_when_kernel(WT* __restrict__ when, long long Np, int M) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += (long long)gridDim.x * blockDim.x)
+    when[i] = (WT)M;
+}
+
+template <typename WT>
+__host__ __device__ constexpr size_t sweep_stage_bytes() { return (size_t)kTilePaths * (8 + 8 + sizeof(WT)); }
+
+// Exercise dates of one quad of paths: uint8 x 4 (one 32-bit word) or uint16 x 4 (one 64-bit word).
+template <typename WT> struct WhenQuad;
+template <> struct WhenQuad<uint8_t> {
   typedef uint32_t Vec;
-  static constexpr int kFlag = 0x80, kMask = 0x7f;
   static __device__ __forceinline__ void unpack(Vec v, int (&w)[4]) {
     w[0] = v & 0xff; w[1] = (v >> 8) & 0xff; w[2] = (v >> 16) & 0xff; w[3] = v >> 24;
   }
   static __device__ __forceinline__ Vec pack(const int (&w)[4]) {
     return (uint32_t)w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16) | ((uint32_t)w[3] << 24);
   }
+  static __device__ __forceinline__ Vec splat(int d) { return 0x01010101u * (uint32_t)d; }
 };
-template <>
-struct WhenQuad<uint16_t> {
+template <> struct WhenQuad<uint16_t> {
   typedef uint2 Vec;
-  static constexpr int kFlag = 0x8000, kMask = 0x7fff;
   static __device__ __forceinline__ void unpack(Vec v, int (&w)[4]) {
     w[0] = v.x & 0xffff; w[1] = v.x >> 16; w[2] = v.y & 0xffff; w[3] = v.y >> 16;
   }
   static __device__ __forceinline__ Vec pack(const int (&w)[4]) {
     return make_uint2((uint32_t)w[0] | ((uint32_t)w[1] << 16), (uint32_t)w[2] | ((uint32_t)w[3] << 16));
   }
+  static __device__ __forceinline__ Vec splat(int d) { return make_uint2(0x00010001u * (uint32_t)d, 0x00010001u * (uint32_t)d); }
 };
 
-struct SweepArgs {
-  const double* paths;  // row m-1 = date m, stride Np
-  void* when;
-  long long Np;
-  double E;
-  int cp, m, M;
-  int first;            // date M: no decision, state := M
-  int lsm;              // PCF_FLAG_AMER_LSM
-  const double* mom_in;
-  double* partials;
-  unsigned int* ticket;
-  double* out;          // kMoments: the 8 moments of date m-1; kFinal: sum, sumsq
-  int* err_flag;
-  int dbg;              // PCF_AMER_DBG (timing experiments only; results are wrong when set)
-};
-
-template <typename WT, bool kMoments, bool kFinal, int kUnroll>
-__global__ void __launch_bounds__(kSweepMaxBlock) amer_sweep_kernel(SweepArgs a, PeerLink link_in, PeerLink link_out) {
+template <typename WT, bool kMoments, bool kFinal, bool kEarly, int kCtas>
+__global__ void __launch_bounds__(kSweepBlock, kCtas) amer_sweep_kernel(SweepArgs a, PeerLink link_in, PeerLink link_out) {
   typedef WhenQuad<WT> WQ;
   typedef typename WQ::Vec WVec;
-  constexpr int kFlag = WQ::kFlag, kMask = WQ::kMask;
+  constexpr int kFlag = WhenBits<WT>::kFlag, kMask = WhenBits<WT>::kMask;
+  constexpr size_t kStage = sweep_stage_bytes<WT>();
+  constexpr int kSums = kFinal ? 2 : 8;
   __shared__ double smem[8 * 2 * 32];
   __shared__ double s_mom[kXchgVals];
   __shared__ double s_coef[3];
   __shared__ int s_mode;  // 0 skip, 1 few-paths branch, 2 regression branch, 3 regression branch (LSM rule)
-  extern __shared__ double s_disc[];  // lanes index it with different k: shared memory, not constant
-  double* s_abs = s_disc + (a.M + 1);
-  for (int k = threadIdx.x; k <= a.M; k += blockDim.x) {
+  __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages];
+  // per-WARP compensated totals (lane 0 of each consumer warp updates its row once per kMomFold tiles)
+  __shared__ double2 s_wacc[kSweepConsumers / 32][kSums];
+  extern __shared__ __align__(128) unsigned char dyn[];
+  unsigned char* ring = dyn;                                                     // stages x kStage
+  double* s_disc = reinterpret_cast<double*>(dyn + (size_t)a.stages * kStage);   // exp(-r dt k), k = 0..M
+  double* s_abs = s_disc + (a.M + 1);                                            // exp(-r k dt) (kFinal)
+  const int tid = threadIdx.x;
+  if (tid < (kSweepConsumers / 32) * kSums) s_wacc[tid / kSums][tid % kSums] = make_double2(0.0, 0.0);
+  for (int k = tid; k <= a.M; k += blockDim.x) {
     s_disc[k] = c_disc_fwd[k];
     if (kFinal) s_abs[k] = c_disc_abs[k];
   }
-  const int m = a.m, cp = a.cp;
-  const double E = a.E;
-  if (!a.first) {
-    // moments of date m: from every rank's publication in this GPU's mailbox (multi-GPU), else local / all-reduced
-    if (link_in.world > 1) {
-      peer_gather<kXchgVals>(link_in, s_mom);
-    } else {
-      if (threadIdx.x < kXchgVals) s_mom[threadIdx.x] = a.mom_in[threadIdx.x];
-      __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kSweepConsumers / 32);
     }
-    if (threadIdx.x == 0) {
-      const double cnt = s_mom[0];
-      if (cnt == 0.0) {
-        s_mode = 0;                       // mc_amer.cpp:73
-      } else if (cnt <= 2.0) {
-        s_mode = 1;                       // mc_amer.cpp:75
-      } else {
-        double coef[3];
-        if (solve3_reference_order(s_mom, coef)) {
-          s_mode = a.lsm ? 3 : 2;
-          s_coef[0] = coef[0]; s_coef[1] = coef[1]; s_coef[2] = coef[2];
-        } else {
-          s_mode = 0;
-          if (blockIdx.x == 0) atomicExch(a.err_flag, PCF_ESINGULAR);  // common.h:115-117
-        }
-      }
-    }
-  } else if (threadIdx.x == 0) {
-    s_mode = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  const int mode = s_mode;
-  const double c0 = s_coef[0], c1 = s_coef[1], c2 = s_coef[2];
-  const bool first = a.first != 0;
 
-  // Everything below works on cx = cp*(S - E) = fma(sgn, S, -sgn*E): bit-identical to the reference's
-  // (double)cp*(S - E) (negation is exact and rounding is symmetric), one DFMA. The regressor x = S - E is
-  // sgn*cx, so x^2, x^4 and y x^2 are sign-free and Sx, Sx^3, Syx are sgn times the sums formed from cx.
-  const double sgn = (double)cp, nE = -sgn * E;
-  const double c1s = c1 * sgn;  // c1*x == (c1*sgn)*cx exactly
-  // per-thread compensated totals live in shared memory (touched once per kMomFold iterations): 32 registers
-  // less per thread, i.e. more resident warps for a kernel whose limiter is DRAM latency
-  __shared__ double2 s_acc[8][kSweepMaxBlock];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) s_acc[k][threadIdx.x] = make_double2(0.0, 0.0);
-  double run[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int cnt = 0, fold = 0;
-  auto fold_runs = [&]() {
-    run[0] += (double)cnt;
-    cnt = 0;
-#pragma unroll
-    for (int k = 0; k < (kFinal ? 2 : 8); ++k) {
-      const double2 t = s_acc[k][threadIdx.x];
-      Comp c(t.x, t.y);
-      c.add(run[k]);
-      s_acc[k][threadIdx.x] = make_double2(c.hi, c.lo);
-      run[k] = 0.0;
-    }
-  };
-  const long long Np = a.Np, quads = Np >> 2;
+  const int m = a.m, cp = a.cp;
+  const double E = a.E;
+  const long long Np = a.Np;
+  const long long ntiles = (Np + kTilePaths - 1) / kTilePaths;
   const double* __restrict__ paths = a.paths;
-  const double2* Sm2 = reinterpret_cast<const double2*>(paths + (size_t)(m - 1) * Np);
-  const double2* Sp2 = reinterpret_cast<const double2*>(paths + (size_t)(kMoments ? m - 2 : 0) * Np);
-  WVec* W = reinterpret_cast<WVec*>(a.when);
-  const int booked = (mode == 2) ? (m | kFlag) : m;  // mode 3 (LSM rule) books the true payoff
+  const double* row_m = paths + (size_t)(m - 1) * Np;
+  const double* row_p = paths + (size_t)(kMoments ? m - 2 : 0) * Np;
+  WT* when = reinterpret_cast<WT*>(a.when);
 
-  const int lane = threadIdx.x & 31;
-  const long long T = (long long)gridDim.x * blockDim.x;
-  // kUnroll quads (4 paths = one 32-byte sector per row) per thread iteration; every streaming load is issued
-  // before the first use. Loop bounds are warp-uniform (the store vote below needs the whole warp).
-  for (long long wb = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < quads; wb += T * kUnroll) {
-    double2 sa[kUnroll], sb[kUnroll], pa[kUnroll], pb[kUnroll];
-    WVec wv[kUnroll];
-    bool live[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const long long i = wb + lane + u * T;
-      live[u] = i < quads;
-      const long long j = live[u] ? i : wb;  // clamp: loads stay in bounds, results are discarded
-      sa[u] = __ldcs(Sm2 + 2 * j);
-      sb[u] = __ldcs(Sm2 + 2 * j + 1);
-      pa[u] = pb[u] = make_double2(0.0, 0.0);
-      if (kMoments) {
-        pa[u] = __ldcs(Sp2 + 2 * j);
-        pb[u] = __ldcs(Sp2 + 2 * j + 1);
+  if (tid >= kSweepConsumers) {
+    // ---- producer warp: one elected lane keeps the ring full; it starts before the moments of date m arrive
+    if (tid == kSweepConsumers) {
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        mbar_wait(&s_empty[s], ph ^ 1);
+        const long long c0 = t * kTilePaths;
+        const uint32_t n = (uint32_t)((Np - c0 < kTilePaths) ? (Np - c0) : kTilePaths);  // multiple of 16
+        unsigned char* st = ring + (size_t)s * kStage;
+        mbar_arrive_expect_tx(&s_full[s], n * (uint32_t)(8 + (kMoments ? 8 : 0) + sizeof(WT)));
+        bulk_g2s(st, row_m + c0, n * 8u, &s_full[s], pol);
+        if (kMoments) bulk_g2s(st + kTilePaths * 8, row_p + c0, n * 8u, &s_full[s], pol);
+        bulk_g2s(st + kTilePaths * 16, when + c0, n * (uint32_t)sizeof(WT), &s_full[s], pol);
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
-      if (!first) wv[u] = W[j];
     }
-    // (b) decisions of date m for every quad of this iteration; `src` ends up holding, per path, the spot whose
-    // payoff is the path's cash flow: S_m when the path exercises at m, else paths[when][n] (gathered below)
-    int w[kUnroll][4];
-    double src[kUnroll][4];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const long long i = wb + lane + u * T;
-      if (first) {
-        w[u][0] = w[u][1] = w[u][2] = w[u][3] = a.M;
-      } else {
-        WQ::unpack(wv[u], w[u]);
+  } else {
+    // ---- consumers: thread `tid` owns paths 4 tid .. 4 tid + 3 of every tile (one 32-byte sector per row)
+    if (!a.first) {
+      // moments of date m: from every rank's publication in this GPU's mailbox (multi-GPU), else local / all-reduced
+      if (link_in.world > 1) {
+        if (tid < 32) peer_gather_warp<kXchgVals>(link_in, s_mom);
+      } else if (tid < kXchgVals) {
+        s_mom[tid] = a.mom_in[tid];
       }
-      src[u][0] = sa[u].x; src[u][1] = sa[u].y; src[u][2] = sb[u].x; src[u][3] = sb[u].y;
-      bool changed = false;
-      if (mode >= 2) {
-        // regression branch, branch-free: every lane evaluates the fit, the update is a select
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const double cx = fma(sgn, src[u][e], nE);  // cp*(S - E); payoff(S) = max(cx, 0)
-          const double yhat = __dadd_rn(__dadd_rn(c0, __dmul_rn(c1s, cx)), __dmul_rn(c2, __dmul_rn(cx, cx)));
-          // reference rule: payoff of the SHIFTED value, payoff(x, E) = max(cp*(x - E), 0) = max(cx - cp*E, 0)
-          // (mc_amer.cpp:100); PCF_FLAG_AMER_LSM (mode 3): the true payoff, cx
-          const double pq = (mode == 2) ? __dadd_rn(cx, nE) : cx;  // before the max(., 0): max(t,0) > y <=> t > y || 0 > y
-          // x == -1 is the reference's sentinel collision (mc_amer.cpp:32,98): such a path is skipped by its pass 2
-          const bool ex = live[u] && cx > 0.0 && !(mode == 2 && cx == -sgn) && (pq > yhat || 0.0 > yhat);
-          w[u][e] = ex ? booked : w[u][e];
-          changed |= ex;
-        }
-      } else if (mode == 1 && live[u]) {
-        // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against the discounted cash flow
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const double pv = payoff(src[u][e], E, cp);
-          if (!(pv > 0.0)) continue;
-          const int d = w[u][e] & kMask;
-          const double cont = __dmul_rn(s_disc[d - m], payoff(__ldg(paths + (size_t)(d - 1) * Np + 4 * i + e), E, cp));
-          if (pv > cont) {
-            w[u][e] = m;
-            changed = true;
+      asm volatile("bar.sync 1, %0;" ::"n"(kSweepConsumers) : "memory");
+      if (tid == 0) {
+        const double cnt = s_mom[0];
+        if (cnt == 0.0) {
+          s_mode = 0;                       // mc_amer.cpp:73
+        } else if (cnt <= 2.0) {
+          s_mode = 1;                       // mc_amer.cpp:75
+        } else {
+          double coef[3];
+          if (solve3_reference_order(s_mom, coef)) {
+            s_mode = a.lsm ? 3 : 2;
+            s_coef[0] = coef[0]; s_coef[1] = coef[1]; s_coef[2] = coef[2];
+          } else {
+            s_mode = 0;
+            if (blockIdx.x == 0) atomicExch(a.err_flag, PCF_ESINGULAR);  // common.h:115-117
           }
         }
       }
-      // whole 128-byte lines back: the warp stores when any of its lanes changed (or initialises at date M)
-      if (__any_sync(0xffffffffu, changed) || first) {
-        if (live[u] && !(a.dbg & 2)) W[i] = WQ::pack(w[u]);
-      }
+    } else if (tid == 0) {
+      s_mode = 0;
     }
-    // (c) gathers of paths[when][n] (mc_amer.cpp:50) for paths whose exercise date is older than m and whose cash
-    // flow is needed: all issued before the first use, so a quad costs one more DRAM round trip, not four
-    double cxp[kUnroll][4];  // cp*(S_{m-1} - E), zeroed when the path is out of the money at m-1
+    asm volatile("bar.sync 1, %0;" ::"n"(kSweepConsumers) : "memory");
+    const int mode = s_mode;
+    // Everything below works on cx = cp*(S - E) = fma(sgn, S, -sgn*E): bit-identical to the reference's
+    // (double)cp*(S - E) (negation is exact and rounding is symmetric), one DFMA. The regressor x = S - E is
+    // sgn*cx, so x^2, x^4 and y x^2 are sign-free and Sx, Sx^3, Syx are sgn times the sums formed from cx.
+    const double sgn = (double)cp, nE = -sgn * E;
+    const double c0 = s_coef[0], c1s = s_coef[1] * sgn, c2 = s_coef[2];  // c1*x == (c1*sgn)*cx exactly
+    // reference rule (mode 2): exercise when payoff(x, E) = max(cp*(x - E), 0) = max(cx + nE, 0) exceeds the fit
+    // (mc_amer.cpp:100), and a path with x == -1 collides with the reference's sentinel and is skipped
+    // (mc_amer.cpp:32,98). PCF_FLAG_AMER_LSM (mode 3): the true payoff cx, no sentinel, books without the flag.
+    const double nE2 = (mode == 2) ? nE : 0.0;
+    const double sentinel = (mode == 2) ? -sgn : __longlong_as_double(0x7ff8000000000000LL);
+    const int booked = (mode == 2) ? (m | kFlag) : m;
+
+    double run[kSums];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const long long i = wb + lane + u * T;
-      const double Sp[4] = {pa[u].x, pa[u].y, pb[u].x, pb[u].y};
+    for (int k = 0; k < kSums; ++k) run[k] = 0.0;
+    int cnt = 0, fold = 0;
+    // Fold: the plain per-thread runs (<= 4 kMomFold terms each) are summed over the warp in a fixed shuffle order
+    // and added to the warp's compensated totals; only lane 0's copy is used.
+    auto fold_runs = [&]() {
+      if (kMoments) run[0] = (double)cnt;
+      cnt = 0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int d = w[u][e] & kMask;
-        bool need = live[u];
-        if (kMoments) {
-          const double c = fma(sgn, Sp[e], nE);
-          need = need && c > 0.0;
-          cxp[u][e] = need ? c : 0.0;
+      for (int k = 0; k < kSums; ++k) {
+        double v = run[k];
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, dlt));
+        if ((tid & 31) == 0) {
+          const double2 t = s_wacc[tid >> 5][k];
+          Comp c(t.x, t.y);
+          c.add(v);
+          s_wacc[tid >> 5][k] = make_double2(c.hi, c.lo);
         }
-        if (need && d != m && !(a.dbg & 1)) src[u][e] = __ldg(paths + (size_t)(d - 1) * Np + 4 * i + e);
-        if (kFinal && !need) w[u][e] = 0;  // date 0: discount slot, never booked (s_abs[0] * 0)
+        run[k] = 0.0;
       }
-    }
-    // (d) moments of date m-1 / final sum. Out-of-the-money (and dead) lanes add exact zeros.
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    };
+    const size_t row_bytes = (size_t)Np * 8;
+    const double* s_disc_m = s_disc - (m - 1);  // s_disc_m[d] = exp(-r dt (d - (m-1)))
+    // address of paths[d][n] for this thread's first path of tile 0 is colp0 + d*row_bytes (row d-1 holds date d)
+    const char* colp0 = reinterpret_cast<const char*>(paths) + (size_t)tid * 32 - row_bytes;
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const unsigned char* st = ring + (size_t)s * kStage;
+      const long long c0t = t * kTilePaths;
+      const bool live = c0t + 4 * tid < Np;  // Np is a multiple of 16: a quad is live or dead as a whole
+      mbar_wait(&s_full[s], ph);
+      const double2 sa = *reinterpret_cast<const double2*>(st + tid * 32);
+      const double2 sb = *reinterpret_cast<const double2*>(st + tid * 32 + 16);
+      double2 pa = make_double2(0.0, 0.0), pb = pa;
+      if (kMoments) {
+        pa = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32);
+        pb = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32 + 16);
+      }
+      WVec wv = *reinterpret_cast<const WVec*>(st + kTilePaths * 16 + tid * sizeof(WVec));
+      // generic-proxy reads of the slot must be ordered before the TMA engine (async proxy) refills it: without
+      // this fence a deep ring at 2 CTAs/SM produced stale reads (observed as run-to-run price noise)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
+      if (++s == a.stages) { s = 0; ph ^= 1; }
+      if (!live) wv = WQ::splat(m);  // dead quad (tail of the last tile): date m, no flag, never in the money
+
+      const double src[4] = {sa.x, sa.y, sb.x, sb.y};
+      double sp[4] = {pa.x, pa.y, pb.x, pb.y};
+      int w[4];
+      WQ::unpack(wv, w);
+      WVec* wp = reinterpret_cast<WVec*>(when + c0t) + tid;
+      const char* colp = colp0 + (size_t)c0t * 8;
+      // (a') cp*(S_m - E), cp*(S_{m-1} - E) and the gathers that are certain: a path out of the money at m cannot
+      // exercise at m, so if its cash flow is needed (in the money at m-1, or the final sum) it comes from
+      // paths[when][n] (mc_amer.cpp:50) with the date it already has. Issued before the decision arithmetic so
+      // that the DRAM round trip overlaps it.
+      double cx[4], ex[4], gv[4];
+      bool need[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int d = w[u][e] & kMask;
-        const double cr = fma(sgn, src[u][e], nE);
-        const double cs = cr > 0.0 ? cr : 0.0;  // payoff(paths[when][n])
+        cx[e] = fma(sgn, src[e], nE);  // payoff(S_m) = max(cx, 0)
+        need[e] = live;
+        ex[e] = 0.0;
         if (kMoments) {
-          const double ex = cxp[u][e];
-          const bool in = ex > 0.0;
-          const double cont = in ? __dmul_rn(s_disc[in ? d - (m - 1) : 0], cs) : 0.0;
-          const double ex2 = __dmul_rn(ex, ex), ex3 = __dmul_rn(ex2, ex), ex4 = __dmul_rn(ex3, ex);
-          const double yx = __dmul_rn(cont, ex), yx2 = __dmul_rn(yx, ex);
-          cnt += in ? 1 : 0;
-          run[1] += ex;
-          run[2] += ex2;
-          run[3] += ex3;
-          run[4] += ex4;
+          const double c = fma(sgn, sp[e], nE);
+          need[e] = live && c > 0.0;
+          ex[e] = need[e] ? c : 0.0;
+        }
+        gv[e] = src[e];
+        if (kEarly && need[e] && !(cx[e] > 0.0))
+          gv[e] = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)(w[e] & kMask) * row_bytes) + e);
+      }
+      // (b) decision of date m
+      if (mode >= 2) {
+        bool changed = false;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double yhat = __dadd_rn(__dadd_rn(c0, __dmul_rn(c1s, cx[e])), __dmul_rn(c2, __dmul_rn(cx[e], cx[e])));
+          const double pq = __dadd_rn(cx[e], nE2);  // before the max(., 0): max(t, 0) > y <=> t > y | 0 > y
+          const bool exer = live & (cx[e] > 0.0) & (cx[e] != sentinel) & ((pq > yhat) | (0.0 > yhat));
+          w[e] = exer ? booked : w[e];
+          changed |= exer;
+        }
+        // whole 128-byte lines back: a warp stores its 128 dates when any of them changed
+        if (__any_sync(0xffffffffu, changed) && live) *wp = WQ::pack(w);
+      } else if (mode == 1 && live) {
+        // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against the discounted cash flow
+        bool changed = false;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (cx[e] > 0.0) {
+            const int d = w[e] & kMask;
+            const double g = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
+            const double cont = __dmul_rn(s_disc[d - m], payoff(g, E, cp));
+            if (cx[e] > cont) {
+              w[e] = m;
+              changed = true;
+            }
+          }
+        }
+        if (changed) *wp = WQ::pack(w);
+      }
+      // (c) the remaining gathers: in the money at m, cash flow needed, yet not exercised at m (frequent under
+      // PCF_FLAG_AMER_LSM and for calls, never for the reference rule's puts)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = w[e] & kMask;
+        if (need[e] && (!kEarly || cx[e] > 0.0) && d != m)
+          gv[e] = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
+      }
+      // (d) moments of date m-1 / final sum. Out-of-the-money (and dead) lanes add exact zeros.
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = w[e] & kMask;
+        const double cr = fma(sgn, gv[e], nE);
+        const double cs = (need[e] && cr > 0.0) ? cr : 0.0;  // payoff(paths[when][n]), 0 when not needed
+        if (kMoments) {
+          const double x1 = ex[e];
+          const double cont = __dmul_rn(s_disc_m[d], cs);  // d >= m: index in [1, M]
+          const double x2 = __dmul_rn(x1, x1), x3 = __dmul_rn(x2, x1), x4 = __dmul_rn(x3, x1);
+          const double yx = __dmul_rn(cont, x1), yx2 = __dmul_rn(yx, x1);
+          cnt += need[e] ? 1 : 0;
+          run[1] += x1;
+          run[2] += x2;
+          run[3] += x3;
+          run[4] += x4;
           run[5] += cont;
           run[6] += yx;
           run[7] += yx2;
         }
         if (kFinal) {
-          // exercise_st (mc_amer.cpp:103): the regression branch booked payoff(x, E) = max(cp*(x - E), 0), x = S - E
+          // exercise_st (mc_amer.cpp:103): the regression branch booked payoff(x, E) = max(cp*(x - E), 0), x = S - E;
+          // a flagged path has cs > 0, a dead lane has w = m (no flag) and cs = 0
           const double sq = __dadd_rn(cs, nE);
-          const double st = (w[u][e] & kFlag) ? (sq > 0.0 ? sq : 0.0) : cs;
-          const double v = (d != 0 && st != 0.0) ? __dmul_rn(s_abs[d], st) : 0.0;
+          const double stv = (w[e] & kFlag) ? (sq > 0.0 ? sq : 0.0) : cs;
+          const double v = __dmul_rn(s_abs[d], stv);
           run[0] += v;
           run[1] += v * v;
         }
       }
+      if (++fold == kMomFold) {
+        fold_runs();
+        fold = 0;
+      }
     }
-    if (++fold == kMomFold) {
-      fold_runs();
-      fold = 0;
-    }
+    fold_runs();
   }
-  fold_runs();
-  Comp acc[8];
+  // warp totals -> block -> grid (block_reduce's own first stage sees one meaningful lane per warp)
+  Comp acc[kSums];
+  if ((tid & 31) == 0 && tid < kSweepConsumers) {
 #pragma unroll
-  for (int k = 0; k < (kFinal ? 2 : 8); ++k) {
-    const double2 t = s_acc[k][threadIdx.x];
-    acc[k] = Comp(t.x, t.y);
+    for (int k = 0; k < kSums; ++k) {
+      const double2 t = s_wacc[tid >> 5][k];
+      acc[k] = Comp(t.x, t.y);
+    }
   }
   if (kMoments) {
+    const double sgn = (double)cp;
     // back from cx-space to the reference's x = S - E: odd powers of x carry the sign of cp
     acc[1].hi *= sgn; acc[1].lo *= sgn;
     acc[3].hi *= sgn; acc[3].lo *= sgn;
     acc[6].hi *= sgn; acc[6].lo *= sgn;
-    grid_reduce<8>(acc, smem, a.partials, a.ticket, a.out, &link_out);
   }
-  if (kFinal) {
-    Comp v[2];
-    v[0] = acc[0]; v[1] = acc[1];
-    grid_reduce<2>(v, smem, a.partials, a.ticket, a.out, &link_out);
-  }
+  __syncthreads();
+  grid_reduce<kSums>(acc, smem, a.partials, a.ticket, a.out, &link_out);
 }
 
-template <typename WT, bool kMoments, bool kFinal>
-static void launch_sweep(int unroll, int grid, int block, size_t smem, cudaStream_t st, const SweepArgs& a,
-                         const PeerLink& li, const PeerLink& lo) {
-  switch (unroll) {
-    case 1: amer_sweep_kernel<WT, kMoments, kFinal, 1><<<grid, block, smem, st>>>(a, li, lo); break;
-    case 2: amer_sweep_kernel<WT, kMoments, kFinal, 2><<<grid, block, smem, st>>>(a, li, lo); break;
-    default: amer_sweep_kernel<WT, kMoments, kFinal, 4><<<grid, block, smem, st>>>(a, li, lo); break;
+template <typename WT, bool kEarly, int kCtas>
+static int launch_sweep2(Ctx& c, bool final_date, int grid, int stages, const SweepArgs& a, const PeerLink& li,
+                         const PeerLink& lo) {
+  const size_t dsm = (size_t)stages * sweep_stage_bytes<WT>() + 2 * sizeof(double) * (a.M + 1);
+  if (final_date) {
+    auto k = amer_sweep_kernel<WT, false, true, kEarly, kCtas>;
+    PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+    k<<<grid, kSweepBlock, dsm, c.stream>>>(a, li, lo);
+  } else {
+    auto k = amer_sweep_kernel<WT, true, false, kEarly, kCtas>;
+    PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+    k<<<grid, kSweepBlock, dsm, c.stream>>>(a, li, lo);
   }
+  return PCF_OK;
+}
+template <typename WT>
+static int launch_sweep(Ctx& c, bool final_date, int grid, int stages, int per_sm, bool early, const SweepArgs& a,
+                        const PeerLink& li, const PeerLink& lo) {
+  if (per_sm >= 3) {
+    return early ? launch_sweep2<WT, true, 3>(c, final_date, grid, stages, a, li, lo)
+                 : launch_sweep2<WT, false, 3>(c, final_date, grid, stages, a, li, lo);
+  }
+  return early ? launch_sweep2<WT, true, 2>(c, final_date, grid, stages, a, li, lo)
+               : launch_sweep2<WT, false, 2>(c, final_date, grid, stages, a, li, lo);
 }
 
-static inline size_t amer_when_bytes(int M) { return M <= WhenQuad<uint8_t>::kMask ? 1 : 2; }
+static inline size_t amer_when_bytes(int M) { return M <= WhenBits<uint8_t>::kMask ? 1 : 2; }
 
 // Host driver for one GPU. Enqueues everything on c.stream; result (sum, sumsq of discounted cash
 // flows over local paths) lands in c.d_out[0..1]; c.d_out[8..23] holds the per-date moment vectors.
@@ -492,7 +615,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   PCF_CUDA(cudaMemcpyToSymbolAsync(c_disc_fwd, fwd, sizeof(double) * (M + 1), 0, cudaMemcpyHostToDevice, c.stream));
   PCF_CUDA(cudaMemcpyToSymbolAsync(c_disc_abs, ab, sizeof(double) * (M + 1), 0, cudaMemcpyHostToDevice, c.stream));
 
-  const long long Np = (Nl + 3) & ~3LL;  // padded row length
+  const long long Np = (Nl + 15) & ~15LL;  // padded row length: 128-byte rows, 16-byte date tiles (TMA granules)
   char* base = (char*)c.workspace + ws_offset;
   double* paths = (double*)base;
   void* when = (void*)(paths + (size_t)M * Np);
@@ -502,6 +625,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   a.adt = (p.r - 0.5 * p.sigma * p.sigma) * dt;
   a.cs = d_replay ? p.sigma : p.sigma * sqrt(dt);
   a.p0 = pairs.begin; a.H = H; a.Np = Np; a.seed = p.seed; a.w = d_replay;
+  a.dbg = getenv("PCF_AMER_DBG") ? atoi(getenv("PCF_AMER_DBG")) : 0;
 
   {
     // per-call table: e^a 2^(+-j/32), a = (r - sigma^2/2) dt, in long double then rounded once
@@ -550,20 +674,27 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   // Backward sweep m = M .. 1 (mc_amer.cpp:23-27, 31, 109-111). Kernel for date m consumes the moments of date m
   // and produces those of date m-1. Peer path: moments travel through the NVLink mailboxes (publish in the
   // producing kernel, gather in the consuming one); NCCL path: an all-reduce of the 8 doubles between two kernels.
-  // Launch shape: PCF_AMER_SWEEP = "<quads per thread>,<threads per CTA>,<CTAs per SM>" (tuning knob).
-  int unroll = 4, block = 128, per_sm = 4;
+  // Launch shape: PCF_AMER_SWEEP = "<ring stages>,<CTAs per SM>,<early gathers 0|1>" (tuning knob).
+  int stages = 2, per_sm = kSweepCtasPerSM, early = 0;
   if (const char* v = getenv("PCF_AMER_SWEEP")) {
-    if (sscanf(v, "%d,%d,%d", &unroll, &block, &per_sm) != 3 || (unroll != 1 && unroll != 2 && unroll != 4) ||
-        block < 32 || block > kSweepMaxBlock || block % 32 != 0 || per_sm < 1) {
+    if (sscanf(v, "%d,%d,%d", &stages, &per_sm, &early) != 3 || stages < 2 || stages > kMaxStages || per_sm < 1 || per_sm > kSweepCtasPerSM) {
       set_last_error("bad PCF_AMER_SWEEP");
       return PCF_EINVAL;
     }
   }
-  const int grid = grid_for(c, (Np / 4 + unroll - 1) / unroll, block, per_sm);
+  const long long ntiles = (Np + kTilePaths - 1) / kTilePaths;
+  const int grid = (int)std::min<long long>(ntiles, (long long)c.sm_count * per_sm);
   const bool w8 = amer_when_bytes(M) == 1;
+  {
+    const int fg = grid_for(c, Np, 256, 8);
+    if (w8) amer_fill_when_kernel<uint8_t><<<fg, 256, 0, c.stream>>>((uint8_t*)when, Np, M);
+    else amer_fill_when_kernel<uint16_t><<<fg, 256, 0, c.stream>>>((uint16_t*)when, Np, M);
+    c.launches++;
+  }
   SweepArgs sa;
   sa.paths = paths; sa.when = when; sa.Np = Np; sa.E = p.E; sa.cp = p.cp; sa.M = M;
   sa.lsm = (p.flags & PCF_FLAG_AMER_LSM) ? 1 : 0;
+  sa.stages = stages;
   sa.dbg = getenv("PCF_AMER_DBG") ? atoi(getenv("PCF_AMER_DBG")) : 0;
   sa.partials = c.d_partials; sa.ticket = c.d_ticket; sa.err_flag = c.d_flag;
   double* mom[2] = {c.d_out + 8, c.d_out + 16};
@@ -576,18 +707,10 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
     sa.mom_in = mom[m & 1];
     if (m < M && !use_peer(c)) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));
     const PeerLink l_out = next_link(c);
-    if (m > 1) {
-      sa.out = mom[(m - 1) & 1];
-      const size_t dsm = sizeof(double) * (M + 1);
-      if (w8) launch_sweep<uint8_t, true, false>(unroll, grid, block, dsm, c.stream, sa, l_in, l_out);
-      else launch_sweep<uint16_t, true, false>(unroll, grid, block, dsm, c.stream, sa, l_in, l_out);
-    } else {
-      sa.out = c.d_out;
-      const size_t dsm = 2 * sizeof(double) * (M + 1);
-      if (w8) launch_sweep<uint8_t, false, true>(unroll, grid, block, dsm, c.stream, sa, l_in, l_out);
-      else launch_sweep<uint16_t, false, true>(unroll, grid, block, dsm, c.stream, sa, l_in, l_out);
-      *final_link = l_out;
-    }
+    sa.out = (m > 1) ? mom[(m - 1) & 1] : c.d_out;
+    if (w8) PCF_TRY(launch_sweep<uint8_t>(c, m == 1, grid, stages, per_sm, early != 0, sa, l_in, l_out));
+    else PCF_TRY(launch_sweep<uint16_t>(c, m == 1, grid, stages, per_sm, early != 0, sa, l_in, l_out));
+    if (m == 1) *final_link = l_out;
     l_in = l_out;
     c.launches++;
   }
@@ -596,7 +719,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
 }
 
 size_t amer_workspace_bytes(long long local_pairs, int M) {
-  size_t Np = (2 * (size_t)local_pairs + 3) & ~(size_t)3;
+  size_t Np = (2 * (size_t)local_pairs + 15) & ~(size_t)15;
   return (size_t)M * Np * 8 + Np * amer_when_bytes(M) + 256;
 }
 

@@ -74,4 +74,31 @@ __device__ __forceinline__ void peer_gather(const PeerLink& L, double* out) {
   __syncthreads();
 }
 
+// Same, called by ONE full warp (warp-specialised kernels whose other warps are busy); ends with __syncwarp().
+template <int K>
+__device__ __forceinline__ void peer_gather_warp(const PeerLink& L, double* out) {
+  static_assert(K <= 32, "one lane per value");
+  const int slot = (int)(L.seq & 1ull);
+  Mailbox* me = L.peer[L.rank];
+  const int t = threadIdx.x & 31;
+  if (t < L.world) {
+    volatile unsigned long long* f = &me->flags[slot][t];
+    unsigned long long spins = 0;
+    while (*f != L.seq) {
+      if (++spins > (1ull << 31)) {
+        me->error = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (t < K) {
+    double s = 0.0;
+    for (int r = 0; r < L.world; ++r) s = __dadd_rn(s, *(volatile double*)&me->vals[slot][r][t]);
+    out[t] = s;
+  }
+  __syncwarp();
+}
+
 }  // namespace pcf

@@ -22,8 +22,14 @@ if what in ("gen", "both"):
         run(f"gen {v}")
     os.environ.pop("PCF_AMER_GEN")
 if what in ("sweep", "both"):
-    for u in (1, 2, 4):
-        for blk, per in ((128, 2), (128, 3), (128, 4), (128, 6), (128, 8), (256, 1), (256, 2), (256, 3), (256, 4)):
-            os.environ["PCF_AMER_SWEEP"] = f"{u},{blk},{per}"
-            run(f"sweep {u},{blk},{per}")
+    shapes = ((2, 3, 0), (2, 3, 1), (3, 3, 0), (2, 2, 0), (2, 2, 1), (3, 2, 1), (4, 2, 0))
+    best = {k: 1e9 for k in shapes}
+    for rep in range(4):  # interleaved: the GPU's clocks drift as it warms up, so no shape is always first
+        for stages, per, early in shapes:
+            os.environ["PCF_AMER_SWEEP"] = f"{stages},{per},{early}"
+            r = pcf.mc_amer(*a, N, 50, "put", seed=1)
+            best[(stages, per, early)] = min(best[(stages, per, early)], r.seconds_kernel)
+            print(f"rep {rep} sweep stages={stages} ctas/sm={per} early={early}: {r.seconds_kernel*1e3:.3f} ms  price {r.price!r}", flush=True)
+    for k, v in best.items():
+        print(f"best stages={k[0]} ctas/sm={k[1]} early={k[2]}: {v*1e3:.3f} ms")
 pcf.shutdown()
