@@ -4,12 +4,12 @@ HOSTCXX   := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off
 CSRC      := parcompfin_b200/csrc
-SRCS      := $(CSRC)/pcf_api.cu $(CSRC)/mc_kernels.cu $(CSRC)/amer_kernels.cu $(CSRC)/binom_kernels.cu $(CSRC)/peaks.cu
+SRCS      := $(CSRC)/pcf_api.cu $(CSRC)/mc_kernels.cu $(CSRC)/amer_kernels.cu $(CSRC)/binom_kernels.cu $(CSRC)/tree_kernels.cu $(CSRC)/peaks.cu
 OBJS      := $(SRCS:.cu=.o) $(CSRC)/fastmath_tables.o
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/pcf.h
 LIB       := parcompfin_b200/libpcf.so
 HOST      := parcompfin_b200/host
-BINS      := bin/mc_eur bin/mc_eur_multi bin/mc_asia bin/mc_amer bin/binom_embar
+BINS      := bin/mc_eur bin/mc_eur_multi bin/mc_asia bin/mc_amer bin/binom_embar bin/binom_vanilla_eur bin/binom_vanilla_amer
 
 .PHONY: all lib bins oracle clean
 all: lib bins oracle

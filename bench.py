@@ -54,6 +54,13 @@ WORKLOADS = {
     "binom_embar": dict(config="binom_embar call 100/100/.05/.2/1, N=1e8 steps (BASELINE config 2)",
                         N=100_000_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
                         kernel="binom_terms_kernel"),
+    # SURVEY 8(f).1 (widening row): algorithmic work = the recurrence as the reference writes it with tabulated powers:
+    # 2 mul + add + IEEE division (10 slots, libdevice) [+ 2 mul, payoff 2, max 1 for the American tree]
+    "binom_vanilla_amer": dict(config="binom_vanilla_amer put 100/100/.05/.2/1, N=1e5 layers (SURVEY 8f.1; the reference "
+                                      "needs ~45 s per tree at this size)",
+                               N=100_000, M=0, steps_per_unit=1, slots=18.0, bound="fp64", unit="node-updates/s",
+                               algo_src="DESIGN 4.5: 2 mul + add + IEEE division 10 + 2 mul + payoff 2 + max 1",
+                               kernel="tree_steps_kernel"),
 }
 
 
@@ -71,6 +78,8 @@ def run_ours_once(pcf, name, seed, N=None):
         return pcf.mc_amer(*a, N, w["M"], "put", seed=seed)
     if name == "binom_embar":
         return pcf.binom(*a, N, "call")
+    if name == "binom_vanilla_amer":
+        return pcf.binom_vanilla_amer(*a, N, "put")
     raise KeyError(name)
 
 
@@ -202,7 +211,7 @@ def roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src):
         ach = units_per_s * w["slots"] * 2 / 1e12
         peak = fp64_dfma_per_s * 2 / 1e12
         return {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "kernel": w["kernel"], "algorithmic": f"{w['slots']:g} FP64 issue slots per unit (SURVEY 8d), FMA = 2 flop",
+                "kernel": w["kernel"], "algorithmic": f"{w['slots']:g} FP64 issue slots per unit ({w.get('algo_src', 'SURVEY 8d')}), FMA = 2 flop",
                 "peak_source": "measured in this run: DFMA-chain microbenchmark (pcf_fp64_peak); MEASURED_PEAKS.json has no FP64 figure"}
     ach = units_per_s * w["bytes"] / 1e9
     peak = hbm_bytes_per_s / 1e9

@@ -125,6 +125,14 @@ PCF_API int pcf_mc_amer(const pcf_params* p, pcf_result* out);
 /* replaces binom() + comb(), reference src/binom_embar.cpp:5-50, include/common.h:63-72          */
 PCF_API int pcf_binom_embar(const pcf_params* p, pcf_result* out);
 
+/* Backward-induction trees: the programs the reference's run-scripts call to produce `comparison`
+ * (runscript_mc_eur.sh:23, runscript_mc_amer.sh:24). N <= 1e7 (the work is N^2/2 node updates). One GPU: the
+ * layers are a serial chain, the path does not shard. `units` = node updates.
+ * replaces binom(), reference src/binom_vanilla_eur.cpp:5-41                                      */
+PCF_API int pcf_binom_vanilla_eur(const pcf_params* p, pcf_result* out);
+/* replaces binom(), reference src/binom_vanilla_amer.cpp:5-42                                     */
+PCF_API int pcf_binom_vanilla_amer(const pcf_params* p, pcf_result* out);
+
 /* --- diagnostics / test support ----------------------------------------------------------------- */
 /* The normal variates the native-mode kernels consume ("normal stream v1"):
  *   Philox4x32-10, key = seed, counter = (index lo, index hi, t/2, stream); X1 = x1:x0, X2 = x3:x2;

@@ -57,6 +57,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_binom_params.argtypes = [_d, _d, _d, _i, _P, _P, _P, _P]
         L.oracle_binom.restype = _d
         L.oracle_binom.argtypes = [_d] * 5 + [_i, _i, _i]
+        L.oracle_binom_tree.restype = _d
+        L.oracle_binom_tree.argtypes = [_d] * 5 + [_i, _i, _i]
         L.oracle_philox4x32_10.argtypes = [ctypes.POINTER(_u32)] * 3
         L.oracle_normal_stream.argtypes = [_u64, _u32, _u64, _ll, _i, _d, _P]
         _lib = L
@@ -156,6 +158,11 @@ def binom_params(r, sigma, T, N):
 
 def binom(S0, E, r, sigma, T, N, payoff_fun, threads=1):
     return lib().oracle_binom(S0, E, r, sigma, T, N, _cp(payoff_fun), threads)
+
+
+def binom_tree(S0, E, r, sigma, T, N, payoff_fun, american=False):
+    """binom_vanilla_eur / binom_vanilla_amer restated (backward induction, O(N^2))."""
+    return lib().oracle_binom_tree(S0, E, r, sigma, T, N, _cp(payoff_fun), 1 if american else 0)
 
 
 def philox4x32_10(ctr, key):

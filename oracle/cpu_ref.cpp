@@ -364,6 +364,36 @@ ORACLE_API double oracle_binom(double S0, double E, double r, double sigma, doub
   return std::exp(-r * T) * result;
 }
 
+// Backward-induction trees: reference src/binom_vanilla_eur.cpp:15-41 and
+// src/binom_vanilla_amer.cpp:15-42. Same lattice parameters as binom_embar; terminal layer
+// v[i] = payoff(S0 u^i d^(N-i)) (eur: max((S-E)*cp, 0) with cp a double, :30; amer: payoff(), :29), then for
+// n = N-1..0, i = 0..n:  v[i] = (p v[i+1] + q v[i]) / R   (eur :35), and for the American tree the max with the
+// immediate payoff payoff(S0 pow(u,i) pow(d,n-i)) (amer :33-35). In place, ascending i, so v[i+1] is still the
+// layer-(n+1) value when v[i] is overwritten.
+ORACLE_API double oracle_binom_tree(double S0, double E, double r, double sigma, double T, int N, int cp,
+                                    int american) {
+  double u, d, p, q;
+  oracle_binom_params(r, sigma, T, N, &u, &d, &p, &q);
+  const double dt = (double)T / (double)N;
+  const double R = std::exp(r * dt);
+  std::vector<double> v(N + 1);
+  for (int i = 0; i <= N; ++i) {
+    const double S = S0 * std::pow(u, i) * std::pow(d, N - i);
+    v[i] = american ? payoff(S, E, cp) : std::max((S - E) * (double)cp, (double)0.0);
+  }
+  for (int n = N - 1; n >= 0; --n)
+    for (int i = 0; i <= n; ++i) {
+      const double jatk = (p * v[i + 1] + q * v[i]) / R;
+      if (american) {
+        const double sij = payoff(S0 * std::pow(u, i) * std::pow(d, n - i), E, cp);
+        v[i] = std::max(jatk, sij);
+      } else {
+        v[i] = jatk;
+      }
+    }
+  return v[0];
+}
+
 // ---------------------------------------------------------------------------------------------
 // CPU restatement of the PRODUCT's counter-based normal stream (include/pcf.h "normal stream v1"),
 // used to check the CUDA generator: Philox4x32-10 (Salmon et al., SC'11; Random123 KAT vectors in

@@ -2,8 +2,8 @@
 // the reference translation unit is #included where it lies (path given by -DREF_SRC), its
 // main() renamed away, and the pricing function is called with argv parsed exactly as the
 // reference's own main does (getArg/getArgD, include/common.h:25-38). Prints "%.17g\n".
-// Built four times by oracle/Makefile with -DREF_mc_eur / -DREF_mc_asia / -DREF_mc_amer /
-// -DREF_binom_embar. The RNG seed is pinned by wrap_time.c (PCF_FIXED_TIME).
+// Built by oracle/Makefile with -DREF_mc_eur / -DREF_mc_asia / -DREF_mc_amer / -DREF_binom_embar /
+// -DREF_binom_vanilla_eur / -DREF_binom_vanilla_amer. The RNG seed is pinned by wrap_time.c (PCF_FIXED_TIME).
 #define main ref_main_unused
 #include REF_SRC
 #undef main
@@ -22,7 +22,7 @@ int main(int argc, char *argv[]) {
   res = mc_asia(S0, E, r, sigma, T, N, getArg(argv, 8), cp);
 #elif defined(REF_mc_amer)
   res = mc_amer(S0, E, r, sigma, T, N, getArg(argv, 8), cp);
-#elif defined(REF_binom_embar)
+#elif defined(REF_binom_embar) || defined(REF_binom_vanilla_eur) || defined(REF_binom_vanilla_amer)
   res = binom(S0, E, r, sigma, T, N, cp);
 #endif
   std::printf("%.17g\n", res);

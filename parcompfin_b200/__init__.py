@@ -31,6 +31,7 @@ EXPORTS = (
     "pcf_init", "pcf_init_rank", "pcf_nccl_unique_id", "pcf_shutdown", "pcf_world_size",
     "pcf_ipc_export", "pcf_ipc_import", "pcf_peer_enable", "pcf_peer_active",
     "pcf_mc_eur", "pcf_mc_eur_multi", "pcf_mc_asia", "pcf_mc_amer", "pcf_binom_embar",
+    "pcf_binom_vanilla_eur", "pcf_binom_vanilla_amer",
     "pcf_normal_stream", "pcf_philox4x32_10", "pcf_chol_equicorr", "pcf_fp64_peak", "pcf_hbm_peak",
     "pcf_device_info", "pcf_strerror", "pcf_last_error",
 )
@@ -91,7 +92,8 @@ def load_library() -> ctypes.CDLL:
             "g.build()'` (there is no CPU fallback)")
     lib = ctypes.CDLL(LIB_PATH)
     P, R = ctypes.POINTER(PcfParams), ctypes.POINTER(PcfResult)
-    for name in ("pcf_mc_eur", "pcf_mc_eur_multi", "pcf_mc_asia", "pcf_mc_amer", "pcf_binom_embar"):
+    for name in ("pcf_mc_eur", "pcf_mc_eur_multi", "pcf_mc_asia", "pcf_mc_amer", "pcf_binom_embar",
+                 "pcf_binom_vanilla_eur", "pcf_binom_vanilla_amer"):
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = [P, R], ctypes.c_int
     lib.pcf_init.argtypes, lib.pcf_init.restype = [ctypes.c_int], ctypes.c_int
@@ -245,6 +247,16 @@ def binom(S0, E, r, sigma, T, N, payoff_fun, *, window=False) -> Result:
     """reference src/binom_embar.cpp:5-50"""
     return _call("pcf_binom_embar", S0, E, r, sigma, T, N, payoff_fun,
                  flags=PCF_FLAG_BINOM_WINDOW if window else 0)
+
+
+def binom_vanilla_eur(S0, E, r, sigma, T, N, payoff_fun) -> Result:
+    """reference src/binom_vanilla_eur.cpp:5-41 (backward-induction tree; `units` = node updates)"""
+    return _call("pcf_binom_vanilla_eur", S0, E, r, sigma, T, N, payoff_fun)
+
+
+def binom_vanilla_amer(S0, E, r, sigma, T, N, payoff_fun) -> Result:
+    """reference src/binom_vanilla_amer.cpp:5-42 (American tree; `units` = node updates)"""
+    return _call("pcf_binom_vanilla_amer", S0, E, r, sigma, T, N, payoff_fun)
 
 
 # ---- diagnostics ---------------------------------------------------------------------------------

@@ -31,6 +31,7 @@ int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host, Shard paths
 int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset,
                 PeerLink* final_link);
 size_t amer_workspace_bytes(long long local_pairs, int M);
+int run_binom_tree(Ctx& c, const pcf_params& p, bool american);
 int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid, const PeerLink& link);
 int run_philox_kat(Ctx& c, const unsigned int ctr[4], const unsigned int key[2], uint32_t* d_out);
 int run_normal_stream(Ctx& c, uint64_t seed, uint32_t stream, uint64_t index0, long long count, int T,
@@ -596,6 +597,47 @@ int pcf_binom_embar(const pcf_params* p, pcf_result* out) {
   out->status = s;
   return s;
 }
+
+// Backward-induction trees. The layers are a serial chain of small, L2-resident rows: the path does not
+// shard, so a multi-GPU job runs it on its first GPU only (every rank of a one-process-per-GPU job computes its own
+// replica: there is nothing to exchange).
+static int binom_tree_call(const pcf_params* p, pcf_result* out, bool american) {
+  int s = check_common(p, out);
+  if (s == PCF_OK && p->N > 10000000LL) s = PCF_EINVAL;  // O(N^2): 5e13 node updates at the cap
+  if (s != PCF_OK) { if (out) out->status = s; return s; }
+  const double t0 = now_s();
+  Ctx& c = g_ctx[0];
+  CallOut o;
+  s = [&]() -> int {
+    PCF_CUDA(cudaSetDevice(c.device));
+    c.launches = 0;
+    PCF_TRY(run_binom_tree(c, *p, american));  // records c.ev0 after the pow tables are resident
+    PCF_CUDA(cudaEventRecord(c.ev1, c.stream));
+    PCF_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    PCF_CUDA(cudaStreamSynchronize(c.stream));
+    float ms = 0.f;
+    PCF_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+    o.vals[0] = c.h_out[0];
+    o.seconds_kernel = ms * 1e-3;
+    o.launches = c.launches;
+    return PCF_OK;
+  }();
+  if (s == PCF_OK) {
+    out->price = o.vals[0];  // binom_vanilla_*.cpp: `return v_ij[0]` (the discounting is inside the recurrence)
+    out->sum = o.vals[0];
+    out->n = p->N + 1;
+    out->units = p->N * (p->N + 1) / 2;  // node updates
+    out->seconds_kernel = o.seconds_kernel;
+    out->launches = o.launches;
+    out->gpus = 1;
+    out->seconds_total = now_s() - t0;
+  }
+  out->status = s;
+  return s;
+}
+
+int pcf_binom_vanilla_eur(const pcf_params* p, pcf_result* out) { return binom_tree_call(p, out, false); }
+int pcf_binom_vanilla_amer(const pcf_params* p, pcf_result* out) { return binom_tree_call(p, out, true); }
 
 // ------------------------------------------------------------------------------------------------
 int pcf_normal_stream(unsigned long long seed, unsigned int stream, unsigned long long index0,

@@ -1,0 +1,229 @@
+// tree_kernels.cu -- the backward-induction binomial trees, sm_100a FP64.
+//   reference src/binom_vanilla_eur.cpp:15-41 (European) and src/binom_vanilla_amer.cpp:15-42 (American):
+//     v_N[i] = payoff(S0 u^i d^(N-i));   v_n[i] = (p v_{n+1}[i+1] + q v_{n+1}[i]) / R   [, max with payoff(S0 u^i d^(n-i))]
+//   The run-scripts call them right before every Monte Carlo sweep to produce `comparison`
+//   (runscript_mc_eur.sh:23, runscript_mc_amer.sh:24); O(N^2), 45 s on the CPU at N = 1e5.
+//
+// Parity contract: every node value is formed with the reference's operations in the reference's order --
+// p*v[i+1] and q*v[i] rounded separately, their sum rounded, the quotient by R rounded (x86-64 has no FMA
+// contraction in the reference build) -- so the root equals the reference's to the last bit:
+//   * u^i and d^j are TABLES computed on the host with the same glibc pow() the reference calls per node
+//     (2(N+1) calls instead of N^2), and S is formed as (S0*pow(u,i))*pow(d,n-i), the reference's association;
+//   * the division by the constant R is q0 = RN(x*z), r = fma(-q0, R, x), q = fma(r, z, q0) with z = RN(1/R):
+//     the value rounded last is (x/R)(1 - delta*eps), |delta*eps| <= 2^-105, i.e. the correctly rounded
+//     quotient unless x/R lies within 2^-105 (relative) of a rounding boundary -- probability ~2^-51 per node,
+//     ~1e-6 per N = 1e5 tree -- or x is subnormal. tests/test_gpu_parity.py states 1e-13 relative and observes
+//     bit equality.
+//
+// Parallelisation: time-skewed (trapezoid) tiling with no intra-step synchronisation. A warp owns 32*kR
+// consecutive nodes of a layer in registers (kR per lane), advances them kSteps layers -- per layer one shuffle
+// brings the right neighbour's first value -- and writes the 32*kR - kSteps left-most nodes, which are the ones
+// whose whole dependency cone was inside the warp. One launch = kSteps layers of the whole tree; layers ping-pong
+// between two HBM (L2-resident) buffers. The American tree also needs d^(n-i): per warp the window of the d-power
+// table that its cone touches is staged in shared memory (padded against bank conflicts) and every lane keeps a
+// kR-entry sliding window of it in registers, refilled with ONE shared load per layer.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+#include "common.cuh"
+#include "binom_math.cuh"
+
+namespace pcf {
+
+struct TreeArgs {
+  const double* vin;   // layer n0: entries 0..n0
+  double* vout;        // layer n0 - steps
+  const double* pu;    // pow(u, i), i = 0..N   (American)
+  const double* pd;    // pow(d, j), j = 0..N   (American)
+  long long n0;
+  int steps;           // <= kSteps
+  double p, q, R, z;   // z = RN(1/R)
+  double S0, sgn, nE;  // payoff(S) = max(fma(sgn, S, nE), 0) = max(cp*(S - E), 0)
+};
+
+// reference: (p*v[i+1] + q*v[i])/R, binom_vanilla_eur.cpp:35 / binom_vanilla_amer.cpp:34
+__device__ __forceinline__ double tree_node(double lo, double hi, const TreeArgs& a) {
+  const double x = __dadd_rn(__dmul_rn(a.p, hi), __dmul_rn(a.q, lo));
+  const double q0 = __dmul_rn(x, a.z);
+  const double r = fma(-q0, a.R, x);
+  return fma(r, a.z, q0);
+}
+
+constexpr int kTreeWarps = 4;  // warps per CTA (independent of each other)
+
+template <int kR, int kSteps, bool kAmer>
+__global__ void __launch_bounds__(kTreeWarps * 32) tree_steps_kernel(TreeArgs a) {
+  constexpr int kL = 32 * kR;            // nodes per warp
+  constexpr int kStride = kL - kSteps;   // nodes a warp finishes
+  constexpr int kWin = kL + kSteps;      // d-power window per warp (unpadded entries)
+  constexpr int kPad = kWin + kWin / 8 + 8;
+  __shared__ double s_pd[kAmer ? kTreeWarps * kPad : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * kTreeWarps + warp;
+  const long long base = gw * kStride;
+  const long long n_out = a.n0 - a.steps;
+  if (base > n_out) return;  // warps are independent: no block-level barrier below
+  const long long i0 = base + (long long)lane * kR;
+
+  double v[kR], A[kR], W[kR];
+#pragma unroll
+  for (int j = 0; j < kR; ++j) {
+    const long long i = i0 + j;
+    v[j] = (i <= a.n0) ? a.vin[i] : 0.0;
+  }
+  // d-power window: entry k holds pd[lo + k], lo = n0 - kSteps - base - kL + 1 (clamped reads below 0 are never used
+  // by a node inside the tree); padded index k + (k >> 3) makes the lane stride 9 doubles (conflict-free LDS.64)
+  double* my_pd = s_pd + (kAmer ? warp * kPad : 0);
+  const long long lo = a.n0 - kSteps - base - kL + 1;
+  if (kAmer) {
+#pragma unroll
+    for (int j = 0; j < kR; ++j) {
+      const long long i = i0 + j;
+      A[j] = (i <= a.n0) ? __dmul_rn(a.S0, a.pu[i]) : 0.0;  // S0*pow(u,i), binom_vanilla_amer.cpp:33
+    }
+    for (int k = lane; k < kWin; k += 32) {
+      const long long idx = lo + k;
+      my_pd[k + (k >> 3)] = (idx >= 0 && idx <= a.n0) ? a.pd[idx] : 0.0;
+    }
+    __syncwarp();
+  }
+  // node (i0 + j) of the layer reached after s+1 steps (n = n0 - 1 - s) needs pd[n - i0 - j] = window entry
+  // k(s, j) = kSteps + kL - 2 - lane*kR - (s + j): it depends on s + j only, so the lane keeps entries t = s..s+kR-1 in
+  // W[t % kR] and replaces the one that falls out of the window with ONE shared load per step.
+  const int kbase = kSteps + kL - 2 - lane * kR;
+  if (kAmer) {
+#pragma unroll
+    for (int t = 0; t < kR; ++t) {
+      const int k = kbase - t;
+      W[t] = my_pd[k + (k >> 3)];
+    }
+  }
+  const int groups = (a.steps + kR - 1) / kR;
+  for (int g = 0; g < groups; ++g) {
+#pragma unroll
+    for (int kk = 0; kk < kR; ++kk) {
+      const int s = g * kR + kk;
+      if (s < a.steps) {  // warp-uniform
+        const double halo = __shfl_down_sync(0xffffffffu, v[0], 1);  // lane 31: outside the cone, never written back
+#pragma unroll
+        for (int j = 0; j < kR; ++j) {
+          const double hi = (j + 1 < kR) ? v[j + 1] : halo;
+          double nv = tree_node(v[j], hi, a);
+          if (kAmer) {
+            // payoff(S0*pow(u,i)*pow(d,n-i)) and std::max(jatk, sij), binom_vanilla_amer.cpp:33-35
+            const double c = fma(a.sgn, __dmul_rn(A[j], W[(kk + j) % kR]), a.nE);
+            const double sij = c > 0.0 ? c : 0.0;
+            nv = (nv < sij) ? sij : nv;
+          }
+          v[j] = nv;
+        }
+        if (kAmer) {
+          const int k = kbase - (s + kR);  // entry t = s + kR replaces t = s
+          W[kk] = (k >= 0) ? my_pd[k + (k >> 3)] : 0.0;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kR; ++j) {
+    const long long i = i0 + j;
+    if (lane * kR + j < kStride && i <= n_out) a.vout[i] = v[j];
+  }
+}
+
+// terminal layer: eur max((S-E)*cp, 0) (binom_vanilla_eur.cpp:30), amer payoff(S,E,cp) (binom_vanilla_amer.cpp:29) --
+// the same value (multiplication by +-1 is exact)
+__global__ void tree_terminal_kernel(double* __restrict__ v, const double* __restrict__ pu, const double* __restrict__ pd,
+                                     long long N, double S0, double sgn, double nE) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= N; i += (long long)gridDim.x * blockDim.x) {
+    const double S = __dmul_rn(__dmul_rn(S0, pu[i]), pd[N - i]);
+    const double c = fma(sgn, S, nE);
+    v[i] = c > 0.0 ? c : 0.0;
+  }
+}
+
+template <int kR, int kSteps>
+static int tree_launch_all(Ctx& c, TreeArgs a, long long N, bool amer, double* buf0, double* buf1) {
+  constexpr int kStride = 32 * kR - kSteps;
+  long long n = N;
+  double* in = buf0;
+  double* out = buf1;
+  while (n > 0) {
+    const int steps = (int)std::min<long long>(kSteps, n);
+    a.vin = in; a.vout = out; a.n0 = n; a.steps = steps;
+    const long long warps = (n - steps + 1 + kStride - 1) / kStride;
+    const int grid = (int)((warps + kTreeWarps - 1) / kTreeWarps);
+    if (amer) tree_steps_kernel<kR, kSteps, true><<<grid, kTreeWarps * 32, 0, c.stream>>>(a);
+    else tree_steps_kernel<kR, kSteps, false><<<grid, kTreeWarps * 32, 0, c.stream>>>(a);
+    c.launches++;
+    n -= steps;
+    std::swap(in, out);
+  }
+  // root -> c.d_out[0]
+  PCF_CUDA(cudaMemcpyAsync(c.d_out, in, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  PCF_CUDA(cudaGetLastError());
+  return PCF_OK;
+}
+
+// pow tables with the reference's own libm call, spread over the host's cores (2(N+1) calls; a serial loop would
+// cost as much as the whole device computation at N = 1e5)
+static void pow_table(double base, long long N, double* out) {
+  unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (N < 4096) nt = 1;
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t)
+    th.emplace_back([=] {
+      for (long long i = t; i <= N; i += nt) out[i] = pow(base, (double)(int)i);  // pow(u,i): i is an int in the reference
+    });
+  for (auto& x : th) x.join();
+}
+
+size_t tree_workspace_bytes(long long N) { return 4 * ((size_t)(N + 1) * sizeof(double) + 256); }
+
+// Enqueues the whole tree on c.stream; root value -> c.d_out[0]. The pow tables are uploaded BEFORE c.ev0 is recorded
+// (inputs resident when the device clock starts); the host clock of the call covers them.
+int run_binom_tree(Ctx& c, const pcf_params& p, bool american) {
+  const long long N = p.N;
+  double u, d, pp, q;
+  binom_lattice(p.r, p.sigma, p.T, N, u, d, pp, q);
+  const double dt = (double)p.T / (double)N;
+  const double R = exp(p.r * dt);
+  PCF_TRY(ctx_reserve(c, tree_workspace_bytes(N)));
+  const size_t slot = (size_t)(N + 1) * sizeof(double) + 256;
+  char* ws = (char*)c.workspace;
+  double* d_pu = (double*)ws;
+  double* d_pd = (double*)(ws + slot);
+  double* buf0 = (double*)(ws + 2 * slot);
+  double* buf1 = (double*)(ws + 3 * slot);
+  std::vector<double> h(2 * (size_t)(N + 1));
+  pow_table(u, N, h.data());
+  pow_table(d, N, h.data() + (N + 1));
+  PCF_CUDA(cudaMemcpyAsync(d_pu, h.data(), (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+  PCF_CUDA(cudaMemcpyAsync(d_pd, h.data() + (N + 1), (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+  PCF_CUDA(cudaStreamSynchronize(c.stream));  // `h` dies with this frame
+  PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+
+  TreeArgs a{};
+  a.pu = d_pu; a.pd = d_pd;
+  a.p = pp; a.q = q; a.R = R; a.z = 1.0 / R;
+  a.S0 = p.S0; a.sgn = (double)p.cp; a.nE = -a.sgn * p.E;
+  tree_terminal_kernel<<<grid_for(c, N + 1, 256, 8), 256, 0, c.stream>>>(buf0, d_pu, d_pd, N, p.S0, a.sgn, a.nE);
+  c.launches++;
+  // launch shape: PCF_TREE = <nodes per lane><layers per launch / 8>  (tuning knob)
+  const char* e = getenv("PCF_TREE");
+  const int shape = e ? atoi(e) : 48;
+  switch (shape) {
+    case 22: return tree_launch_all<2, 16>(c, a, N, american, buf0, buf1);
+    case 44: return tree_launch_all<4, 32>(c, a, N, american, buf0, buf1);
+    case 48: return tree_launch_all<4, 64>(c, a, N, american, buf0, buf1);
+    case 88: return tree_launch_all<8, 64>(c, a, N, american, buf0, buf1);
+    case 84: return tree_launch_all<8, 32>(c, a, N, american, buf0, buf1);
+    default:
+      set_last_error("unknown PCF_TREE");
+      return PCF_EINVAL;
+  }
+}
+
+}  // namespace pcf

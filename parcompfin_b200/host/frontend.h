@@ -127,7 +127,7 @@ typedef int (*pcf_method)(const pcf_params*, pcf_result*);
 
 // Runs one method the way every reference main does: parse -> start clock -> price -> report.
 inline int run(const char* what, pcf_method fn, pcf_params p, const std::string& payoff_fun, int gpus,
-               const Clock& overall, int M_field, int assets_field) {
+               const Clock& overall, int M_field, int assets_field, const char* method = "CUDA") {
   std::vector<double> replay = env_replay();
   if (!replay.empty()) {
     p.replay = replay.data();
@@ -139,7 +139,7 @@ inline int run(const char* what, pcf_method fn, pcf_params p, const std::string&
   check(fn(&p, &res));
   double t_calc = calc.seconds();
   double t_all = overall.seconds();
-  reporting("CUDA", payoff_fun, p.S0, p.E, p.r, p.sigma, p.T, t_all, t_calc, res.price,
+  reporting(method, payoff_fun, p.S0, p.E, p.r, p.sigma, p.T, t_all, t_calc, res.price,
             env_double("PCF_COMPARISON", 0.0), p.N, res.gpus, M_field, assets_field);
   verbose(what, res);
   pcf_shutdown();

@@ -126,8 +126,32 @@ def exact_binom_windowed(out):
                             "first weight from mpmath loggamma")
 
 
+def tree_vectors():
+    """binom_vanilla_eur / binom_vanilla_amer: outputs of the compiled reference (%.17g) and the
+    published Serial_vanilla rows of results/results_binom_embar.csv (10 digits)."""
+    out = {"_generated_by": "tests/golden/make_golden.py trees", "binom_vanilla_eur": [], "binom_vanilla_amer": [],
+           "binom_vanilla_eur_csv": []}
+    cases = [("call", (100, 100, 0.05, 0.2, 1)), ("put", (100, 100, 0.05, 0.2, 1)),
+             ("call", (100, 110, 0.02, 0.75, 1)), ("put", (100, 90, 0.02, 0.75, 1)), ("put", (80, 100, 0.1, 0.3, 2.5))]
+    for pf, P in cases:
+        for N in (1, 2, 3, 7, 31, 32, 33, 64, 100, 191, 192, 193, 1000, 4000, 10000):
+            for prog in ("binom_vanilla_eur", "binom_vanilla_amer"):
+                if prog.endswith("amer") and N > 4000 and P[0] != 100:
+                    continue
+                out[prog].append({"payoff": pf, "params": P, "N": N, "price": oracle.ref_fn(prog, pf, *P, N)})
+                print(prog, pf, P, N, out[prog][-1]["price"], flush=True)
+    for line in open("/root/reference/results/results_binom_embar.csv"):
+        f = line.strip().split(",")
+        if len(f) >= 14 and f[0] == "Serial_vanilla" and f[1] in ("call", "put"):
+            out["binom_vanilla_eur_csv"].append({"payoff": f[1], "params": [float(x) for x in f[2:7]], "N": int(f[7]),
+                                                 "price": float(f[13]), "source": "results/results_binom_embar.csv"})
+    return out
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ref", "exact"]
+    which = sys.argv[1:] or ["ref", "exact", "trees"]
+    if "trees" in which:
+        json.dump(tree_vectors(), open(os.path.join(HERE, "tree_vectors.json"), "w"), indent=1)
     if "ref" in which:
         json.dump(reference_vectors(), open(os.path.join(HERE, "reference_vectors.json"), "w"), indent=1)
     if "exact" in which:

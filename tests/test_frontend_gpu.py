@@ -42,16 +42,20 @@ def test_row_format_matches_reference_layout(tmp_path):
     ("mc_amer", ("put", 100, 100, 0.05, 0.2, 1, 100000, 50), ("50", "1")),
     ("mc_eur_multi", ("call", 100, 100, 0.05, 0.2, 1, 100000, 16, 0.5), ("0", "16")),
     ("binom_embar", ("call", 100, 110, 0.02, 0.75, 1, 1000), ("0", "1")),
+    ("binom_vanilla_eur", ("call", 100, 110, 0.02, 0.75, 1, 1000), ("0", "1")),
+    ("binom_vanilla_amer", ("put", 100, 100, 0.05, 0.2, 1, 2000), ("0", "1")),
 ])
 def test_every_front_end_prints_one_row(prog, args, nfield):
     rc, out, err = run(prog, *args, env={"PCF_SEED": "7"})
     assert rc == 0, err
     fields = out.split(",")
-    assert len(fields) == 16 and fields[0] == "CUDA" and fields[1] == args[0]
+    assert len(fields) == 16 and fields[0] == ("CUDA_vanilla" if "vanilla" in prog else "CUDA") and fields[1] == args[0]
     assert (fields[8], fields[10]) == nfield
     assert math.isfinite(float(fields[13]))
-    if prog == "binom_embar":
-        assert fields[13] == "26.60882645"  # reference results/results_binom_embar.csv, N = 1000
+    if prog in ("binom_embar", "binom_vanilla_eur"):
+        assert fields[13] == "26.60882645"  # reference results/results_binom_embar.csv, N = 1000 (both rows)
+    if prog == "binom_vanilla_amer":
+        assert fields[13] == "6.090232044"  # oracle/_ref/binom_vanilla_amer put 100 100 0.05 0.2 1 2000
 
 
 def test_error_behaviour_matches_reference():

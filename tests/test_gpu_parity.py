@@ -261,6 +261,56 @@ def test_binom_full_size_properties(gpu, golden):
 
 # ---------------------------------------------------------------------------------------------------
 # size-independent properties at larger sizes, edge cases, error behaviour
+def test_trees_match_reference_vectors(gpu, golden):
+    # SURVEY 8f.1. Every node is formed with the reference's operations in the reference's order; the only liberty is
+    # the division by the constant R (csrc/tree_kernels.cu), exact unless a quotient lies within 2^-105 of a rounding
+    # boundary. Stated tolerance 1e-13 relative; observed: bit-equal on every vector.
+    exact = total = 0
+    for prog, fn in (("binom_vanilla_eur", gpu.binom_vanilla_eur), ("binom_vanilla_amer", gpu.binom_vanilla_amer)):
+        for c in golden["tree_vectors"][prog]:
+            g = fn(*c["params"], c["N"], c["payoff"])
+            assert abs(g.price - c["price"]) <= 1e-13 * max(1.0, abs(c["price"])), (prog, c, g.price)
+            assert g.units == c["N"] * (c["N"] + 1) // 2
+            exact += g.price == c["price"]
+            total += 1
+    assert exact == total, (exact, total)
+
+
+def test_trees_match_published_csv(gpu, golden):
+    # reference results/results_binom_embar.csv, Serial_vanilla rows, N = 100 .. 100000 (45.6 s there at N = 1e5)
+    for c in golden["tree_vectors"]["binom_vanilla_eur_csv"]:
+        g = gpu.binom_vanilla_eur(*c["params"], c["N"], c["payoff"])
+        assert f"{g.price:.10g}" == f"{c['price']:.10g}", c
+
+
+def test_trees_launch_shape_independence_and_properties(gpu, monkeypatch):
+    # the tiling (nodes per lane x layers per launch) must not change a single bit: same operations per node
+    P = (100, 100, .05, .2, 1)
+    ref = {}
+    for shape in ("44", "22", "48", "88", "84"):
+        monkeypatch.setenv("PCF_TREE", shape)
+        for N in (1, 5, 31, 97, 1000, 5003):
+            for pf in ("call", "put"):
+                e = gpu.binom_vanilla_eur(*P, N, pf).price
+                a = gpu.binom_vanilla_amer(*P, N, pf).price
+                assert ref.setdefault((N, pf), (e, a)) == (e, a), (shape, N, pf)
+    monkeypatch.delenv("PCF_TREE")
+    # small trees against the oracle, including N not a multiple of anything
+    for N in (1, 2, 3, 17, 200, 777):
+        for pf in ("call", "put"):
+            assert gpu.binom_vanilla_eur(*P, N, pf).price == oracle.binom_tree(*P, N, pf, False)
+            assert gpu.binom_vanilla_amer(*P, N, pf).price == oracle.binom_tree(*P, N, pf, True)
+    # full size (the reference needs 45 s per tree here): the European tree and the binomial formula price the same
+    # lattice; early exercise is worth something for the put and nothing for the call (r > 0, no dividends)
+    N = 100_000
+    e_put, a_put = gpu.binom_vanilla_eur(*P, N, "put").price, gpu.binom_vanilla_amer(*P, N, "put").price
+    e_call, a_call = gpu.binom_vanilla_eur(*P, N, "call").price, gpu.binom_vanilla_amer(*P, N, "call").price
+    assert rel(e_call, gpu.binom(*P, N, "call").price) < 1e-9 and rel(e_put, gpu.binom(*P, N, "put").price) < 1e-9
+    assert 6.08 < a_put < 6.10 and a_put > e_put + 0.4          # binom_vanilla_amer put 100/100/.05/.2/1 -> 6.0903
+    assert rel(a_call, e_call) < 1e-12
+    assert rel(e_call - e_put, 100 - 100 * math.exp(-0.05)) < 1e-8   # put-call parity on the lattice
+
+
 def test_determinism_and_homogeneity(gpu):
     a = gpu.mc_asia(*P1, 2_000_000, 252, "call", seed=11)
     b = gpu.mc_asia(*P1, 2_000_000, 252, "call", seed=11)

@@ -95,6 +95,26 @@ def test_binom_matches_published_csv(golden):
         assert rel(got, c["price"]) < 1e-9, c
 
 
+def test_trees_match_reference(golden):
+    # binom_vanilla_eur / binom_vanilla_amer restated: bit-exact against the compiled reference
+    for prog, american in (("binom_vanilla_eur", False), ("binom_vanilla_amer", True)):
+        n = 0
+        for c in golden["tree_vectors"][prog]:
+            if c["N"] > (1000 if american else 4000):
+                continue
+            assert oracle.binom_tree(*c["params"], c["N"], c["payoff"], american) == c["price"], (prog, c)
+            n += 1
+        assert n >= 40
+
+
+def test_trees_match_published_csv(golden):
+    rows = [c for c in golden["tree_vectors"]["binom_vanilla_eur_csv"] if c["N"] <= 3200]
+    assert len(rows) >= 5
+    for c in rows:
+        got = oracle.binom_tree(*c["params"], c["N"], c["payoff"], False)
+        assert f"{got:.10g}" == f"{c['price']:.10g}", c
+
+
 def test_binom_converges_to_black_scholes():
     assert abs(oracle.binom(100, 100, .05, .2, 1, 4000, "call") - BS_CALL) < 2e-3
     assert abs(oracle.binom(100, 100, .05, .2, 1, 4000, "put") - BS_PUT) < 2e-3
