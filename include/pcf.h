@@ -117,6 +117,27 @@ PCF_API int pcf_world_size(void);
 PCF_API int pcf_mc_eur(const pcf_params* p, pcf_result* out);
 /* replaces mc_eur() + mvnorm(), reference src/mc_eur_multi.cpp:6-35, include/mvn.h:42-82        */
 PCF_API int pcf_mc_eur_multi(const pcf_params* p, pcf_result* out);
+/* General basket: the same pricing loop (src/mc_eur_multi.cpp:23-34) with what the reference hard-wires
+ * made explicit. Every pointer is a HOST array and may be NULL, which selects the reference's value:
+ *   S0[d], sigma[d]  per-asset spot / volatility           (NULL: p->S0 / p->sigma for every asset, :30)
+ *   weight[d]        basket weights                        (NULL: 1/d, :30)
+ *   cov[d*d]         row-major symmetric covariance of the driving normals (NULL: equicorrelation p->rho,
+ *                    include/mvn.h:55-60); factored as mvn.h:63-76 does: Cholesky, else eigenvectors * sqrt(eigenvalues)
+ *                    when only positive SEMI-definite; PCF_ENOTPD when it has a negative eigenvalue
+ *   transform[d*d]   row-major A with Bt = A Z, overrides cov (what mvn.h calls normTransform); replay parity tests
+ *                    hand the oracle and the GPU the same A
+ * d = p->assets. Replay layout as pcf_mc_eur_multi: Z[n*d + a]. */
+typedef struct pcf_basket {
+  const double* S0;
+  const double* sigma;
+  const double* weight;
+  const double* cov;
+  const double* transform;
+} pcf_basket;
+PCF_API int pcf_mc_basket(const pcf_params* p, const pcf_basket* b, pcf_result* out);
+/* The factor pcf_mc_basket builds from `cov` (host computation): A A^T = cov. *used_eigen = 1 when the Cholesky
+ * factorisation failed and the eigen-decomposition of mvn.h:72-76 was used (A is then a full matrix). */
+PCF_API int pcf_normal_transform(int d, const double* cov, double* A, int* used_eigen);
 /* replaces mc_asia(),  reference src/mc_asia.cpp:5-40                                            */
 PCF_API int pcf_mc_asia(const pcf_params* p, pcf_result* out);
 /* replaces mc_amer() + pathsfinder() + inverse()/mat_vec_mul(), reference src/mc_amer.cpp:5-114,

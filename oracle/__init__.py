@@ -48,6 +48,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_chol_equicorr.argtypes = [_i, _d, _P]
         L.oracle_mc_basket.restype = _d
         L.oracle_mc_basket.argtypes = [_d] * 5 + [_ll, _i, _i, _d, _P, _P, _P, ctypes.POINTER(_i)]
+        L.oracle_mc_basket_general.restype = _d
+        L.oracle_mc_basket_general.argtypes = [_P, _d, _d, _P, _d, _ll, _i, _i, _P, _P, _P, _P, _P]
         L.oracle_mc_basket_omp_timed.restype = _d
         L.oracle_mc_basket_omp_timed.argtypes = [_d] * 5 + [_ll, _i, _i, _d, _u64, _i, _P]
         L.oracle_mc_asia_omp_timed.restype = _d
@@ -128,6 +130,20 @@ def mc_basket(S0, E, r, sigma, T, N, payoff_fun, d, rho, Z, moments=False):
                                    ctypes.byref(s2), ctypes.byref(st))
     if st.value:
         raise ValueError("not positive definite")
+    return (price, s.value, s2.value) if moments else price
+
+
+def mc_basket_general(S0, E, r, sigma, T, N, payoff_fun, A, weights, Z, moments=False):
+    """per-asset spots/vols/weights and a full d x d normal transform A (Bt = A Z)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    d = A.shape[0]
+    S0 = np.ascontiguousarray(np.broadcast_to(np.asarray(S0, dtype=np.float64), (d,)))
+    sg = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (d,)))
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    Z = np.ascontiguousarray(Z, dtype=np.float64)
+    s, s2 = _d(), _d()
+    price = lib().oracle_mc_basket_general(_p(S0), E, r, _p(sg), T, N, _cp(payoff_fun), d, _p(A), _p(w), _p(Z),
+                                           ctypes.byref(s), ctypes.byref(s2))
     return (price, s.value, s2.value) if moments else price
 
 

@@ -296,6 +296,33 @@ ORACLE_API double oracle_mc_basket(double S0, double E, double r, double sigma, 
   return basket_core(S0, E, r, sigma, T, N, cp, d, L.data(), Z, sum_out, sumsq_out, false);
 }
 
+// the same pricing loop (mc_eur_multi.cpp:23-34) with what the reference hard-wires made explicit:
+// a FULL d x d normal transform A (mvn.h:66-76: the Cholesky factor, or eigenvectors * sqrt(eigenvalues) when the
+// matrix is only positive semi-definite), per-asset spot, volatility and weight. Bt = A * Z, Z[n*d + a].
+ORACLE_API double oracle_mc_basket_general(const double* S0, double E, double r, const double* sigma, double T,
+                                           long long N, int cp, int d, const double* A, const double* w,
+                                           const double* Z, double* sum_out, double* sumsq_out) {
+  double acc = 0, acc2 = 0;
+  std::vector<double> bt((size_t)d);
+  for (long long n = 0; n < N; ++n) {
+    const double* z = Z + n * (long long)d;
+    for (int a = 0; a < d; ++a) {
+      double s = 0;
+      for (int k = 0; k < d; ++k) s += A[(size_t)a * d + k] * z[k];
+      bt[a] = s;
+    }
+    double basket = 0;
+    for (int a = 0; a < d; ++a)
+      basket += w[a] * S0[a] * std::exp((r - sigma[a] * sigma[a] / 2) * T + sigma[a] * bt[a]);
+    double v = payoff(basket, E, cp);
+    acc += v;
+    acc2 += v * v;
+  }
+  if (sum_out) *sum_out = acc;
+  if (sumsq_out) *sumsq_out = acc2;
+  return (std::exp(-r * T) * acc) / (double)N;
+}
+
 // Timing-only twin with the OpenMP placement of reference src/mc_eur_multi_omp.cpp:31-46: the
 // sample generation stays serial (mvnorm is called outside the parallel region), the payoff loop is
 // `omp for schedule(dynamic,1000) reduction(+)`. Draws its own mt19937 normals (d*N of them).

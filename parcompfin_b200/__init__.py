@@ -31,7 +31,7 @@ EXPORTS = (
     "pcf_init", "pcf_init_rank", "pcf_nccl_unique_id", "pcf_shutdown", "pcf_world_size",
     "pcf_ipc_export", "pcf_ipc_import", "pcf_peer_enable", "pcf_peer_active",
     "pcf_mc_eur", "pcf_mc_eur_multi", "pcf_mc_asia", "pcf_mc_amer", "pcf_binom_embar",
-    "pcf_binom_vanilla_eur", "pcf_binom_vanilla_amer",
+    "pcf_binom_vanilla_eur", "pcf_binom_vanilla_amer", "pcf_mc_basket", "pcf_normal_transform",
     "pcf_normal_stream", "pcf_philox4x32_10", "pcf_chol_equicorr", "pcf_fp64_peak", "pcf_hbm_peak",
     "pcf_device_info", "pcf_strerror", "pcf_last_error",
 )
@@ -47,6 +47,10 @@ class PcfParams(ctypes.Structure):
         ("replay", ctypes.POINTER(ctypes.c_double)), ("replay_len", ctypes.c_longlong),
         ("flags", ctypes.c_uint),
     ]
+
+
+class PcfBasket(ctypes.Structure):
+    _fields_ = [(n, ctypes.POINTER(ctypes.c_double)) for n in ("S0", "sigma", "weight", "cov", "transform")]
 
 
 class PcfResult(ctypes.Structure):
@@ -96,6 +100,10 @@ def load_library() -> ctypes.CDLL:
                  "pcf_binom_vanilla_eur", "pcf_binom_vanilla_amer"):
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = [P, R], ctypes.c_int
+    lib.pcf_mc_basket.argtypes, lib.pcf_mc_basket.restype = [P, ctypes.POINTER(PcfBasket), R], ctypes.c_int
+    lib.pcf_normal_transform.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                         ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
+    lib.pcf_normal_transform.restype = ctypes.c_int
     lib.pcf_init.argtypes, lib.pcf_init.restype = [ctypes.c_int], ctypes.c_int
     lib.pcf_init_rank.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
     lib.pcf_init_rank.restype = ctypes.c_int
@@ -203,7 +211,7 @@ def shard_of(units: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def _call(fn_name, S0, E, r, sigma, T, N, payoff_fun, M=0, assets=1, rho=0.0, seed=0, replay=None,
-          flags=0) -> Result:
+          flags=0, basket=None) -> Result:
     lib = load_library()
     p = PcfParams()
     p.S0, p.E, p.r, p.sigma, p.T = float(S0), float(E), float(r), float(sigma), float(T)
@@ -215,7 +223,10 @@ def _call(fn_name, S0, E, r, sigma, T, N, payoff_fun, M=0, assets=1, rho=0.0, se
         p.replay = keep.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
         p.replay_len = keep.size
     out = PcfResult()
-    _check(getattr(lib, fn_name)(ctypes.byref(p), ctypes.byref(out)))
+    if basket is not None:
+        _check(getattr(lib, fn_name)(ctypes.byref(p), ctypes.byref(basket), ctypes.byref(out)))
+    else:
+        _check(getattr(lib, fn_name)(ctypes.byref(p), ctypes.byref(out)))
     return Result(out.price, out.sum, out.sumsq, out.std_error, out.n, out.units, out.seconds_kernel,
                   out.seconds_total, out.launches, out.gpus)
 
@@ -229,6 +240,45 @@ def mc_eur_multi(S0, E, r, sigma, T, N, payoff_fun, assets, rho, *, seed=0, repl
     """reference src/mc_eur_multi.cpp:6-35 (the function is also called mc_eur there)"""
     return _call("pcf_mc_eur_multi", S0, E, r, sigma, T, N, payoff_fun, assets=assets, rho=rho,
                  seed=seed, replay=replay)
+
+
+def mc_basket(S0, E, r, sigma, T, N, payoff_fun, assets, *, rho=0.0, weights=None, cov=None, transform=None,
+              seed=0, replay=None) -> Result:
+    """General basket (include/pcf.h pcf_mc_basket): ``S0`` and ``sigma`` may be scalars (the reference's
+    case, src/mc_eur_multi.cpp:30) or length-``assets`` arrays; ``weights`` defaults to 1/d; ``cov`` is the d x d
+    covariance of the driving normals (default: equicorrelation ``rho``, include/mvn.h:55-60) and ``transform`` an
+    explicit factor A (Bt = A Z) that overrides it."""
+    d = int(assets)
+    keep = []
+
+    def arr(x, shape):
+        if x is None:
+            return None
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), shape))
+        if a.shape != shape:
+            raise ValueError("basket array has the wrong shape")
+        keep.append(a)
+        return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+    b = PcfBasket()
+    b.S0 = arr(S0, (d,)) if np.ndim(S0) else None
+    b.sigma = arr(sigma, (d,)) if np.ndim(sigma) else None
+    b.weight, b.cov, b.transform = arr(weights, (d,)), arr(cov, (d, d)), arr(transform, (d, d))
+    s0 = float(np.ravel(S0)[0])
+    sg = float(np.ravel(sigma)[0])
+    return _call("pcf_mc_basket", s0, E, r, sg, T, N, payoff_fun, assets=d, rho=rho, seed=seed, replay=replay,
+                 basket=b)
+
+
+def normal_transform(cov) -> tuple[np.ndarray, bool]:
+    """The factor A (A A^T = cov) the basket kernel uses, and whether the eigen fallback of mvn.h:72-76 produced it."""
+    cov = np.ascontiguousarray(cov, dtype=np.float64)
+    d = cov.shape[0]
+    A = np.zeros((d, d), dtype=np.float64)
+    eig = ctypes.c_int()
+    P = ctypes.POINTER(ctypes.c_double)
+    _check(load_library().pcf_normal_transform(d, cov.ctypes.data_as(P), A.ctypes.data_as(P), ctypes.byref(eig)))
+    return A, bool(eig.value)
 
 
 def mc_asia(S0, E, r, sigma, T, N, M, payoff_fun, *, seed=0, replay=None) -> Result:

@@ -74,6 +74,14 @@ int launch_xchg_finish(Ctx& c, const PeerLink& l, int k, double* d_out);  // d_o
 int ctx_reserve(Ctx& c, size_t bytes);  // ensures c.workspace >= bytes
 int allreduce_sum(Ctx& c, double* d_buf, int count);  // in place, on c.stream; no-op if world == 1
 
+// Host-side description of a general basket, all arrays of length d
+struct BasketHost {
+  const double* S0;
+  const double* sigma;
+  const double* weight;
+  bool full;  // the transform is a full matrix (eigen fallback), not a lower triangle
+};
+
 // Contiguous block partition of `units` over the job: rank g takes
 // [g*ceil(U/G), min(U,(g+1)*ceil(U/G))).
 struct Shard {

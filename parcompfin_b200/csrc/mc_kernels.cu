@@ -277,6 +277,10 @@ int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay
 // L (row-major, lower) sits in constant memory: every lane reads the same L[a][k] at the same
 // time, which is the constant cache's broadcast case.
 __constant__ double c_L[PCF_MAX_ASSETS * PCF_MAX_ASSETS];
+// per-asset parameters of the general kernel; the reference's basket has one sigma, S0 and weight 1/d
+__constant__ double c_bsig[PCF_MAX_ASSETS];    // sigma_a
+__constant__ double c_bdrift[PCF_MAX_ASSETS];  // (r - sigma_a^2/2) T
+__constant__ double c_bw[PCF_MAX_ASSETS];      // w_a * S0_a
 
 struct BasketArgs {
   double E, drift, sigma;  // drift = (r - sigma^2/2) T   (no sqrt(T) anywhere: SURVEY F9)
@@ -287,7 +291,8 @@ struct BasketArgs {
   const double* Z;  // replay: Z[(n-n0)*d + a]
 };
 
-template <int D, bool kReplay>
+// kFull: the normal transform is a full matrix (eigen-decomposition fallback of mvn.h:72-76), not a lower triangle
+template <int D, bool kReplay, bool kFull>
 __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const MathTables* __restrict__ tables,
                                                            PeerLink link, double* partials, unsigned int* ticket,
                                                            double* out) {
@@ -316,10 +321,10 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const M
           normal_pair(key, (uint64_t)n, (uint32_t)j, PCF_STREAM_BASKET, tv, hc, z0, z1);
         }
 #pragma unroll
-        for (int i = 2 * j; i < D; ++i) bt[i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j], z0, bt[i]);
+        for (int i = kFull ? 0 : 2 * j; i < D; ++i) bt[i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j], z0, bt[i]);
         if (2 * j + 1 < D) {
 #pragma unroll
-          for (int i = 2 * j + 1; i < D; ++i)
+          for (int i = kFull ? 0 : 2 * j + 1; i < D; ++i)
             bt[i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j + 1], z1, bt[i]);
         }
       }
@@ -327,7 +332,7 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const M
     double basket = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i)
-      if (i < a.d) basket = fma(a.wS0, exp_table(fma(a.sigma, bt[i], a.drift), tv), basket);  // :30
+      if (i < a.d) basket = fma(c_bw[i], exp_table(fma(c_bsig[i], bt[i], c_bdrift[i]), tv), basket);  // :30
     double v = payoff(basket, a.E, a.cp);
     s1.add(v);
     s2.add(v * v);
@@ -403,19 +408,34 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) mc_basket_equi_kernel(Bask
 }
 
 template <int D>
-static void launch_basket(Ctx& c, const BasketArgs& a, int grid, bool replay, const PeerLink& link) {
-  if (replay)
-    mc_basket_kernel<D, true><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
-  else
-    mc_basket_kernel<D, false><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+static void launch_basket(Ctx& c, const BasketArgs& a, int grid, bool replay, bool full, const PeerLink& link) {
+#define PCF_BK(R, F) mc_basket_kernel<D, R, F><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out)
+  if (replay) { if (full) PCF_BK(true, true); else PCF_BK(true, false); }
+  else { if (full) PCF_BK(false, true); else PCF_BK(false, false); }
+#undef PCF_BK
 }
 
+// `spec` == nullptr: the reference's basket (one sigma, one S0, weights 1/d). Otherwise per-asset arrays of length d and
+// `full` says whether L_host is a full matrix (eigen fallback) or a lower triangle.
 int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-major */,
-                  Shard paths, const double* d_replay, const PeerLink& link) {
+                  Shard paths, const double* d_replay, const PeerLink& link, const BasketHost* spec) {
   const int d = p.assets;
+  const bool full = spec && spec->full;
   double Lpad[PCF_MAX_ASSETS * PCF_MAX_ASSETS] = {0};
   for (int i = 0; i < d; ++i)
-    for (int k = 0; k <= i; ++k) Lpad[i * PCF_MAX_ASSETS + k] = L_host[i * d + k];
+    for (int k = 0; k < (full ? d : i + 1); ++k) Lpad[i * PCF_MAX_ASSETS + k] = L_host[i * d + k];
+  {
+    double sg[PCF_MAX_ASSETS] = {0}, dr[PCF_MAX_ASSETS] = {0}, w[PCF_MAX_ASSETS] = {0};
+    for (int i = 0; i < d; ++i) {
+      const double s_i = spec ? spec->sigma[i] : p.sigma;
+      sg[i] = s_i;
+      dr[i] = (p.r - s_i * s_i / 2) * p.T;
+      w[i] = spec ? spec->weight[i] * spec->S0[i] : (1.0 / (double)d) * p.S0;
+    }
+    PCF_CUDA(cudaMemcpyToSymbolAsync(c_bsig, sg, sizeof(sg), 0, cudaMemcpyHostToDevice, c.stream));
+    PCF_CUDA(cudaMemcpyToSymbolAsync(c_bdrift, dr, sizeof(dr), 0, cudaMemcpyHostToDevice, c.stream));
+    PCF_CUDA(cudaMemcpyToSymbolAsync(c_bw, w, sizeof(w), 0, cudaMemcpyHostToDevice, c.stream));
+  }
   PCF_CUDA(cudaMemcpyToSymbolAsync(c_L, Lpad, sizeof(Lpad), 0, cudaMemcpyHostToDevice, c.stream));
   BasketArgs a;
   a.E = p.E; a.sigma = p.sigma; a.cp = p.cp; a.d = d;
@@ -425,7 +445,7 @@ int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-m
   a.seed = p.seed; a.Z = d_replay;
   const bool rp = d_replay != nullptr;
   // constant columns below the diagonal (bitwise)? -> equicorrelation fast path
-  bool equi = !rp && !getenv("PCF_BASKET_GENERAL");
+  bool equi = !rp && !spec && !getenv("PCF_BASKET_GENERAL");
   for (int k = 0; k < d && equi; ++k)
     for (int i = k + 2; i < d; ++i)
       if (L_host[i * d + k] != L_host[(k + 1) * d + k]) { equi = false; break; }
@@ -464,11 +484,11 @@ int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-m
     return PCF_OK;
   }
   int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
-  if (d <= 2) launch_basket<2>(c, a, grid, rp, link);
-  else if (d <= 4) launch_basket<4>(c, a, grid, rp, link);
-  else if (d <= 8) launch_basket<8>(c, a, grid, rp, link);
-  else if (d <= 16) launch_basket<16>(c, a, grid, rp, link);
-  else launch_basket<32>(c, a, grid, rp, link);
+  if (d <= 2) launch_basket<2>(c, a, grid, rp, full, link);
+  else if (d <= 4) launch_basket<4>(c, a, grid, rp, full, link);
+  else if (d <= 8) launch_basket<8>(c, a, grid, rp, full, link);
+  else if (d <= 16) launch_basket<16>(c, a, grid, rp, full, link);
+  else launch_basket<32>(c, a, grid, rp, full, link);
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;

@@ -27,7 +27,7 @@ namespace pcf {
 int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, const PeerLink& link);
 int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay, const PeerLink& link);
 int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host, Shard paths, const double* d_replay,
-                  const PeerLink& link);
+                  const PeerLink& link, const BasketHost* spec);
 int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset,
                 PeerLink* final_link);
 size_t amer_workspace_bytes(long long local_pairs, int M);
@@ -488,16 +488,11 @@ int pcf_chol_equicorr(int d, double rho, double* L) {
   return PCF_OK;
 }
 
-int pcf_mc_eur_multi(const pcf_params* p, pcf_result* out) {
-  int s = check_common(p, out);
-  if (s == PCF_OK && (p->assets < 1 || p->assets > PCF_MAX_ASSETS)) s = PCF_EINVAL;
-  if (s == PCF_OK && p->replay && p->replay_len < p->N * (long long)p->assets) s = PCF_EINVAL;
-  double L[PCF_MAX_ASSETS * PCF_MAX_ASSETS];
-  if (s == PCF_OK) s = pcf_chol_equicorr(p->assets, p->rho, L);
-  if (s != PCF_OK) { if (out) out->status = s; return s; }
+// Shared driver of the two basket entry points. `spec` == nullptr: the reference's basket.
+static int basket_call(const pcf_params* p, const double* L, const BasketHost* spec, pcf_result* out) {
   const double t0 = now_s();
   std::vector<CallOut> co(g_ctx.size());
-  s = for_each_ctx([&](Ctx& c) -> int {
+  int s = for_each_ctx([&](Ctx& c) -> int {
     CallOut& o = co[&c - &g_ctx[0]];
     c.launches = 0;
     Shard sh = shard_of(p->N, c.rank, c.world);
@@ -506,7 +501,7 @@ int pcf_mc_eur_multi(const pcf_params* p, pcf_result* out) {
       PCF_TRY(upload_replay(c, p->replay, sh.begin * p->assets, sh.size() * p->assets, 0, &d_rep));
     PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
     const PeerLink l = next_link(c);
-    PCF_TRY(run_mc_basket(c, *p, L, sh, d_rep, l));
+    PCF_TRY(run_mc_basket(c, *p, L, sh, d_rep, l, spec));
     PCF_TRY(finish_call(c, l, 2, o.vals, &o.seconds_kernel, &o.flag));
     o.launches = c.launches;
     return PCF_OK;
@@ -514,6 +509,118 @@ int pcf_mc_eur_multi(const pcf_params* p, pcf_result* out) {
   if (s == PCF_OK) fill_mc_result(out, co, std::exp(-p->r * p->T), p->N, p->N, t0);
   out->status = s;
   return s;
+}
+
+int pcf_mc_eur_multi(const pcf_params* p, pcf_result* out) {
+  int s = check_common(p, out);
+  if (s == PCF_OK && (p->assets < 1 || p->assets > PCF_MAX_ASSETS)) s = PCF_EINVAL;
+  if (s == PCF_OK && p->replay && p->replay_len < p->N * (long long)p->assets) s = PCF_EINVAL;
+  double L[PCF_MAX_ASSETS * PCF_MAX_ASSETS];
+  if (s == PCF_OK) s = pcf_chol_equicorr(p->assets, p->rho, L);
+  if (s != PCF_OK) { if (out) out->status = s; return s; }
+  return basket_call(p, L, nullptr, out);
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric d x d matrix (row-major): V's columns are the eigenvectors,
+// lam the eigenvalues. d <= 32, so a few sweeps of d(d-1)/2 rotations on the host.
+static void jacobi_eigen(int d, const double* Sin, double* V, double* lam) {
+  std::vector<double> A(Sin, Sin + (size_t)d * d);
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) V[i * d + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < d; ++i)
+      for (int j = 0; j < d; ++j) (i == j ? diag : off) += A[i * d + j] * A[i * d + j];
+    if (off <= 1e-30 * diag || off == 0.0) break;
+    for (int pi = 0; pi < d - 1; ++pi)
+      for (int q = pi + 1; q < d; ++q) {
+        const double apq = A[pi * d + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q * d + q] - A[pi * d + pi]) / (2 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+        const double cs = 1 / std::sqrt(t * t + 1), sn = t * cs;
+        for (int k = 0; k < d; ++k) {  // columns pi, q of A
+          const double akp = A[k * d + pi], akq = A[k * d + q];
+          A[k * d + pi] = cs * akp - sn * akq;
+          A[k * d + q] = sn * akp + cs * akq;
+        }
+        for (int k = 0; k < d; ++k) {  // rows pi, q of A
+          const double apk = A[pi * d + k], aqk = A[q * d + k];
+          A[pi * d + k] = cs * apk - sn * aqk;
+          A[q * d + k] = sn * apk + cs * aqk;
+        }
+        for (int k = 0; k < d; ++k) {
+          const double vkp = V[k * d + pi], vkq = V[k * d + q];
+          V[k * d + pi] = cs * vkp - sn * vkq;
+          V[k * d + q] = sn * vkp + cs * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < d; ++i) lam[i] = A[i * d + i];
+}
+
+int pcf_normal_transform(int d, const double* cov, double* A, int* used_eigen) {
+  if (d < 1 || d > PCF_MAX_ASSETS || !cov || !A) return PCF_EINVAL;
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < i; ++j) {
+      const double a = cov[i * d + j], b = cov[j * d + i];
+      if (!(std::fabs(a - b) <= 1e-12 * (std::fabs(a) + std::fabs(b)) || a == b)) return PCF_EINVAL;  // also rejects NaN
+    }
+  if (used_eigen) *used_eigen = 0;
+  // row-by-row Cholesky of the lower triangle (mvn.h:63-70)
+  std::memset(A, 0, sizeof(double) * d * d);
+  bool pd = true;
+  for (int i = 0; i < d && pd; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = cov[i * d + j];
+      for (int k = 0; k < j; ++k) s -= A[i * d + k] * A[j * d + k];
+      if (i == j) {
+        if (!(s > 0.0)) { pd = false; break; }
+        A[i * d + i] = std::sqrt(s);
+      } else {
+        A[i * d + j] = s / A[j * d + j];
+      }
+    }
+  if (pd) return PCF_OK;
+  // mvn.h:72-76: eigenvectors * sqrt(eigenvalues). Eigenvalues in [-tol, 0) are rounding noise of a semi-definite matrix
+  // and count as 0 (Eigen's cwiseSqrt would give NaN there); anything more negative is not a covariance matrix.
+  std::vector<double> V((size_t)d * d), lam(d);
+  jacobi_eigen(d, cov, V.data(), lam.data());
+  double lmax = 0;
+  for (int i = 0; i < d; ++i) lmax = std::max(lmax, std::fabs(lam[i]));
+  for (int i = 0; i < d; ++i)
+    if (!(lam[i] >= -1e-10 * lmax)) return PCF_ENOTPD;
+  for (int i = 0; i < d; ++i)
+    for (int k = 0; k < d; ++k) A[i * d + k] = V[i * d + k] * std::sqrt(std::max(lam[k], 0.0));
+  if (used_eigen) *used_eigen = 1;
+  return PCF_OK;
+}
+
+int pcf_mc_basket(const pcf_params* p, const pcf_basket* b, pcf_result* out) {
+  int s = check_common(p, out);
+  if (s == PCF_OK && (!b || p->assets < 1 || p->assets > PCF_MAX_ASSETS)) s = PCF_EINVAL;
+  if (s == PCF_OK && p->replay && p->replay_len < p->N * (long long)p->assets) s = PCF_EINVAL;
+  const int d = (s == PCF_OK) ? p->assets : 0;
+  double A[PCF_MAX_ASSETS * PCF_MAX_ASSETS];
+  double S0[PCF_MAX_ASSETS], sg[PCF_MAX_ASSETS], w[PCF_MAX_ASSETS];
+  int eig = 0;
+  if (s == PCF_OK) {
+    if (b->transform) std::memcpy(A, b->transform, sizeof(double) * d * d);
+    else if (b->cov) s = pcf_normal_transform(d, b->cov, A, &eig);
+    else s = pcf_chol_equicorr(d, p->rho, A);
+  }
+  if (s != PCF_OK) { if (out) out->status = s; return s; }
+  bool full = eig != 0;
+  if (b->transform)
+    for (int i = 0; i < d; ++i)
+      for (int k = i + 1; k < d; ++k) full = full || A[i * d + k] != 0.0;
+  for (int i = 0; i < d; ++i) {
+    S0[i] = b->S0 ? b->S0[i] : p->S0;
+    sg[i] = b->sigma ? b->sigma[i] : p->sigma;
+    w[i] = b->weight ? b->weight[i] : 1.0 / (double)d;
+  }
+  BasketHost spec{S0, sg, w, full};
+  return basket_call(p, A, &spec, out);
 }
 
 int pcf_mc_amer(const pcf_params* p, pcf_result* out) {

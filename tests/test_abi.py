@@ -61,6 +61,30 @@ def test_chol_equicorr_is_host_side():
         pcf.chol_equicorr(3, -0.9)
 
 
+def test_normal_transform_is_host_side():
+    # SURVEY 8f.4 / include/mvn.h:63-76: Cholesky when positive definite, eigenvectors * sqrt(eigenvalues) otherwise
+    import numpy as np
+    rng = np.random.default_rng(1)
+    B = rng.standard_normal((12, 12))
+    cov = B @ B.T / 12 + 0.1 * np.eye(12)
+    A, eig = pcf.normal_transform(cov)
+    assert not eig and np.allclose(A, np.linalg.cholesky(cov), atol=1e-13) and np.allclose(np.triu(A, 1), 0)
+    # rank-deficient (positive SEMI-definite): rho = 1 and rho = -1/(d-1)
+    for d, rho in [(5, 1.0), (4, -1.0 / 3.0), (32, 1.0)]:
+        cov = (1 - rho) * np.eye(d) + rho * np.ones((d, d))
+        A, eig = pcf.normal_transform(cov)
+        assert eig and np.allclose(A @ A.T, cov, atol=1e-12), (d, rho)
+    B = rng.standard_normal((9, 3))
+    cov = B @ B.T  # rank 3 of 9
+    A, eig = pcf.normal_transform(cov)
+    assert eig and np.allclose(A @ A.T, cov, atol=1e-12)
+    with pytest.raises(ValueError):  # a negative eigenvalue is not a covariance matrix
+        pcf.normal_transform(np.array([[1.0, 2.0], [2.0, 1.0]]))
+    with pytest.raises(ValueError):  # asymmetric
+        pcf.normal_transform(np.array([[1.0, 0.5], [0.2, 1.0]]))
+    assert ctypes.sizeof(pcf.PcfBasket) == 40
+
+
 def test_compute_without_init_or_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():

@@ -63,3 +63,37 @@ def test_error_behaviour_matches_reference():
     assert rc != 0 and out == "" and "Unknown payoff function" in err      # src/mc_eur.cpp:42
     rc, out, err = run("mc_amer", "put", 100, 100, 0.05, 0.2, 1, 1001, 10)
     assert rc != 0 and out == "" and "divisible by 2" in err              # include/common.h:180
+
+
+def test_comparison_header_is_read_at_run_time(tmp_path):
+    # the reference's run-scripts rewrite include/comparison.h and rebuild (runscript_mc_eur.sh:22-25); the CUDA front
+    # ends read that file from the working directory instead
+    (tmp_path / "include").mkdir()
+    (tmp_path / "include" / "comparison.h").write_text("#pragma once\ndouble comparison = 26.61224;\n")
+    p = subprocess.run([os.path.join(BIN, "binom_embar"), "call", "100", "110", "0.02", "0.75", "1", "1000"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    f = p.stdout.strip().split(",")
+    assert p.returncode == 0 and f[13] == "26.60882645"
+    assert f[15] == f"{26.60882645 - 26.61224:.10g}"[:len(f[15])] or abs(float(f[15]) - (float(f[13]) - 26.61224)) < 1e-9
+    assert float(f[14]) == abs(float(f[15]))
+
+
+def test_runscript_cuda_appends_reference_format_rows(tmp_path):
+    # the CUDA leg of runscript.sh -- same header, same sweep parameters, one CUDA row per (N, gpus)
+    env = dict(os.environ, RESULTS_DIR=str(tmp_path), PCF_NS="10000 80000", PCF_SEED="3")
+    p = subprocess.run(["bash", os.path.join(ROOT, "runscript_cuda.sh"), "all"], cwd=ROOT, env=env,
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    header = "Method,Payoff,S0,E,r,sigma,T,N,M,Parallel,Nr_of_assets,T_overall,T_calculation,Result,Abs_Error,Error"
+    want = {"binom_embar": 4, "mc_eur": 2, "mc_eur_multi": 2, "mc_amer": 2, "mc_asia": 2}
+    for method, nrows in want.items():
+        lines = (tmp_path / f"results_{method}.csv").read_text().strip().splitlines()
+        assert lines[0] == header                                          # runscript_mc_eur.sh:13
+        rows = [l.split(",") for l in lines[1:]]
+        assert len(rows) == nrows and all(len(r) == 16 for r in rows)
+        assert all(r[0] in ("CUDA", "CUDA_vanilla") and r[1] == "call" and r[2] == "100" for r in rows)
+        assert [r[7] for r in rows if r[0] == "CUDA"] == ["10000", "80000"]
+    amer = [l.split(",") for l in (tmp_path / "results_mc_amer.csv").read_text().strip().splitlines()[1:]]
+    # comparison was baked from the American tree at N = 10000: Error = Result - comparison, |.| in Abs_Error
+    assert all(abs(float(r[14]) - abs(float(r[15]))) < 1e-12 and float(r[14]) < 2.0 for r in amer)
+    assert all(r[8] == "200" for r in amer)

@@ -145,6 +145,44 @@ def test_basket_equicorrelation_fast_path_is_bit_identical(gpu, monkeypatch):
         assert rel(fast.sum, gen.sum) < 1e-14 and rel(fast.sumsq, gen.sumsq) < 1e-14, (d, rho)
 
 
+def test_general_basket_replay_vs_oracle(gpu):
+    # per-asset spots/vols/weights and a general covariance; oracle and GPU share the factor A
+    rng = np.random.default_rng(11)
+    for d, N, pf, kind in [(16, 40000, "call", "chol"), (5, 20001, "put", "chol"), (32, 3000, "call", "chol"),
+                           (9, 20000, "call", "semidef"), (4, 10000, "put", "rho1"), (1, 5000, "call", "chol")]:
+        S0 = rng.uniform(80, 120, d); sg = rng.uniform(.1, .4, d); w = rng.dirichlet(np.ones(d))
+        if kind == "chol":
+            B = rng.standard_normal((d, d)); cov = B @ B.T / d + .2 * np.eye(d)
+        elif kind == "semidef":
+            B = rng.standard_normal((d, 3)); cov = B @ B.T  # rank 3: Cholesky fails, mvn.h:72-76 fallback
+        else:
+            cov = np.ones((d, d))
+        A, eig = gpu.normal_transform(cov)
+        assert eig == (kind != "chol") and np.allclose(A @ A.T, cov, atol=1e-12)
+        Z = oracle.normals_mt19937(100 + d, 1.0, N * d)
+        o, so, so2 = oracle.mc_basket_general(S0, 100, .03, sg, 1, N, pf, A, w, Z, moments=True)
+        g = gpu.mc_basket(S0, 100, .03, sg, 1, N, pf, d, weights=w, cov=cov, replay=Z)
+        assert rel(g.price, o) < REPLAY_TOL and rel(g.sumsq, so2) < REPLAY_TOL, (d, kind)
+        g2 = gpu.mc_basket(S0, 100, .03, sg, 1, N, pf, d, weights=w, transform=A, replay=Z)
+        assert g2.sum == g.sum
+    # every array NULL = the reference's basket: same numbers as pcf_mc_eur_multi on the same Philox stream
+    a = gpu.mc_basket(100, 100, .05, .2, 1, 200_001, "call", 16, rho=0.5, seed=9)
+    b = gpu.mc_eur_multi(100, 100, .05, .2, 1, 200_001, "call", 16, 0.5, seed=9)
+    assert rel(a.sum, b.sum) < 1e-13 and rel(a.sumsq, b.sumsq) < 1e-13
+    # native mode, heterogeneous basket: GPU price within 3 standard errors of the oracle on an independent stream
+    d, N = 8, 400_000
+    S0 = rng.uniform(80, 120, d); sg = rng.uniform(.1, .4, d); w = rng.dirichlet(np.ones(d))
+    B = rng.standard_normal((d, d)); cov = B @ B.T / d + .2 * np.eye(d)
+    A, _ = gpu.normal_transform(cov)
+    g = gpu.mc_basket(S0, 100, .03, sg, 1, N, "call", d, weights=w, cov=cov, seed=4)
+    o, so, so2 = oracle.mc_basket_general(S0, 100, .03, sg, 1, N, "call", A, w,
+                                          oracle.normals_mt19937(77, 1.0, N * d), moments=True)
+    se_o = math.exp(-.03) * math.sqrt((so2 / N - (so / N) ** 2) / N)
+    assert abs(g.price - o) < 3 * math.hypot(g.std_error, se_o)
+    with pytest.raises(ValueError):
+        gpu.mc_basket(100, 100, .05, .2, 1, 1000, "call", 2, cov=np.array([[1.0, 2.0], [2.0, 1.0]]))
+
+
 def test_basket_cholesky_matches_oracle(gpu):
     for d, rho in [(16, 0.5), (32, 0.99), (5, -0.2)]:
         assert np.abs(gpu.chol_equicorr(d, rho) - oracle.chol_equicorr(d, rho)).max() < 1e-15

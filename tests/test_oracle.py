@@ -141,6 +141,29 @@ def test_basket_anchors():
         oracle.chol_equicorr(4, -0.5)  # not positive definite (rho < -1/(d-1))
 
 
+def test_general_basket_reduces_to_reference_basket():
+    # with one sigma, one S0, weights 1/d and A = chol(equicorrelation) the general restatement IS the
+    # reference loop (src/mc_eur_multi.cpp:23-34) -- same operations up to the order of the 1/d * S0 product
+    N, d, rho = 20000, 6, 0.4
+    Z = oracle.normals_mt19937(9, 1.0, N * d)
+    a = oracle.mc_basket(100, 95, .05, .25, 1, N, "put", d, rho, Z)
+    L = oracle.chol_equicorr(d, rho)
+    b = oracle.mc_basket_general(100, 95, .05, .25, 1, N, "put", L, np.full(d, 1.0 / d), Z)
+    assert rel(b, a) < 1e-13
+    # a permutation of (asset, weight, spot, vol, row of A) leaves the price unchanged up to summation order
+    rng = np.random.default_rng(3)
+    S0 = rng.uniform(80, 120, d); sg = rng.uniform(.1, .4, d); w = rng.dirichlet(np.ones(d))
+    B = rng.standard_normal((d, d)); A = np.linalg.cholesky(B @ B.T / d + .2 * np.eye(d))
+    perm = rng.permutation(d)
+    p0 = oracle.mc_basket_general(S0, 100, .03, sg, 1, N, "call", A, w, Z)
+    p1 = oracle.mc_basket_general(S0[perm], 100, .03, sg[perm], 1, N, "call", A[perm], w[perm], Z)
+    assert rel(p1, p0) < 1e-12
+    # a single asset with weight 1 and A = [[1]] is mc_eur at T = 1
+    z = Z[:N]
+    assert rel(oracle.mc_basket_general(100, 100, .05, .2, 1, N, "call", np.eye(1), [1.0], z),
+               oracle.mc_eur(100, 100, .05, .2, 1, N, "call", z)) < 1e-15
+
+
 def test_basket_published_statistical_pin():
     # reference results/results_mc_eur_multi.csv: d=4, rho=.5, call 100/100 r=.1 sigma=.2 T=1 -> 11.92 (+-0.01)
     N = 400000
