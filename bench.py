@@ -54,6 +54,12 @@ WORKLOADS = {
     "binom_embar": dict(config="binom_embar call 100/100/.05/.2/1, N=1e8 steps (BASELINE config 2)",
                         N=100_000_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
                         kernel="binom_terms_kernel"),
+    # the same sum with the screening pass off (PCF_FLAG_BINOM_NOSCREEN): every pair through the full-accuracy routine;
+    # bit-identical result (tests/test_gpu_parity.py), reported so that the shortcut's share is visible
+    "binom_embar_noscreen": dict(config="binom_embar call 100/100/.05/.2/1, N=1e8 steps, screening pass OFF "
+                                        "(every term pair through the full-accuracy saddle-point routine)",
+                                 N=100_000_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
+                                 kernel="binom_terms_kernel"),
     # SURVEY 8(f).1 (widening row): algorithmic work = the recurrence as the reference writes it with tabulated powers:
     # 2 mul + add + IEEE division (10 slots, libdevice) [+ 2 mul, payoff 2, max 1 for the American tree]
     "binom_vanilla_amer": dict(config="binom_vanilla_amer put 100/100/.05/.2/1, N=1e5 layers (SURVEY 8f.1; the reference "
@@ -78,6 +84,8 @@ def run_ours_once(pcf, name, seed, N=None):
         return pcf.mc_amer(*a, N, w["M"], "put", seed=seed)
     if name == "binom_embar":
         return pcf.binom(*a, N, "call")
+    if name == "binom_embar_noscreen":
+        return pcf.binom(*a, N, "call", screen=False)
     if name == "binom_vanilla_amer":
         return pcf.binom_vanilla_amer(*a, N, "put")
     raise KeyError(name)

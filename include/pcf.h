@@ -49,6 +49,12 @@ typedef enum pcf_status {
                                       continuation value and book that payoff. Off by default: parity with the
                                       reference means reproducing its rule.                                     */
 
+#define PCF_FLAG_BINOM_NOSCREEN 0x4u /* binom_embar: evaluate every term pair with the full-accuracy saddle-point
+                                      routine. By default a pair is first screened with a two-logarithm evaluation of
+                                      its log-weights (abs. error < 1e-4) and settled as 0 when both are below the
+                                      underflow rule's threshold with margin; the sum is bit-identical either way
+                                      (tests assert it), the flag exists so both rates can be reported.            */
+
 /* Normal-stream ids (word 3 of the Philox counter), one per method. */
 #define PCF_STREAM_EUR 0u
 #define PCF_STREAM_ASIA 1u

@@ -23,6 +23,7 @@ PCF_OK, PCF_EINVAL_PAYOFF, PCF_EODD_N, PCF_ESINGULAR, PCF_EINVAL, PCF_ENOTPD = 0
 PCF_ECUDA, PCF_ENCCL, PCF_ENOINIT, PCF_ENOMEM = 10, 11, 12, 13
 PCF_FLAG_BINOM_WINDOW = 0x1
 PCF_FLAG_AMER_LSM = 0x2
+PCF_FLAG_BINOM_NOSCREEN = 0x4
 STREAM_EUR, STREAM_ASIA, STREAM_BASKET, STREAM_AMER = 0, 1, 2, 3
 MAX_ASSETS = 32
 
@@ -293,10 +294,11 @@ def mc_amer(S0, E, r, sigma, T, N, M, payoff_fun, *, seed=0, replay=None, lsm=Fa
                  flags=PCF_FLAG_AMER_LSM if lsm else 0)
 
 
-def binom(S0, E, r, sigma, T, N, payoff_fun, *, window=False) -> Result:
-    """reference src/binom_embar.cpp:5-50"""
+def binom(S0, E, r, sigma, T, N, payoff_fun, *, window=False, screen=True) -> Result:
+    """reference src/binom_embar.cpp:5-50. ``screen=False`` (PCF_FLAG_BINOM_NOSCREEN) sends every term pair through
+    the full-accuracy routine; the result is bit-identical, only slower."""
     return _call("pcf_binom_embar", S0, E, r, sigma, T, N, payoff_fun,
-                 flags=PCF_FLAG_BINOM_WINDOW if window else 0)
+                 flags=(PCF_FLAG_BINOM_WINDOW if window else 0) | (0 if screen else PCF_FLAG_BINOM_NOSCREEN))
 
 
 def binom_vanilla_eur(S0, E, r, sigma, T, N, payoff_fun) -> Result:

@@ -19,7 +19,7 @@ namespace pcf {
 
 constexpr int kBinomBlock = 256;
 
-__global__ void __launch_bounds__(kBinomBlock) binom_terms_kernel(BinomArgs a, const MathTables* __restrict__ tables,
+__global__ void __launch_bounds__(kBinomBlock, 4) binom_terms_kernel(BinomArgs a, const MathTables* __restrict__ tables,
                                                                   PeerLink link, double* partials,
                                                                   unsigned int* ticket, double* out) {
   __shared__ double smem[1 * 2 * 32];
@@ -36,7 +36,17 @@ __global__ void __launch_bounds__(kBinomBlock) binom_terms_kernel(BinomArgs a, c
     acc.add(end_terms(a, tv));
     i += T;
   }
-  for (; i < a.i1; i += T) acc.add(pair_terms(i, a, tv, hc));
+  if (a.screen) {
+    // the loop carries x and N-x as doubles (exact below 2^53): no 64-bit integer conversions per pair
+    double x = (double)i, nx = (double)(a.N - i);
+    const double step = (double)T;
+    for (; i < a.i1; i += T, x += step, nx -= step) {
+      if (pair_dead(x, nx, a, tv, hc)) continue;  // both weights underflow: the pair adds exactly 0.0
+      acc.add(pair_terms(i, a, tv, hc));
+    }
+  } else {
+    for (; i < a.i1; i += T) acc.add(pair_terms(i, a, tv, hc));
+  }
   if (a.add_mid && tid == 0)  // x == N-x: both halves of the pair are the same term (binom_embar.cpp:42-45)
     acc.add(0.5 * pair_terms(a.N / 2, a, tv, hc));
   Comp v[1] = {acc};
@@ -48,6 +58,7 @@ int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid, const Peer
   BinomArgs a;
   fill_binom_args(p.S0, p.E, p.r, p.sigma, p.T, p.N, p.cp, a);
   a.i0 = pairs.begin; a.i1 = pairs.end; a.add_mid = add_mid ? 1 : 0;
+  a.screen = (p.flags & PCF_FLAG_BINOM_NOSCREEN) ? 0 : 1;
   PCF_CUDA(cudaMemcpyToSymbolAsync(c_sfe, a.sfe, sizeof(a.sfe), 0, cudaMemcpyHostToDevice, c.stream));
   int grid = grid_for(c, pairs.size(), kBinomBlock, 4);
   binom_terms_kernel<<<grid, kBinomBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket,

@@ -39,6 +39,7 @@ struct TreeArgs {
   const double* pd;    // pow(d, j), j = 0..N   (American)
   long long n0;
   int steps;           // <= kSteps
+  int trig;            // programmatic dependent launch: 1 = release the next launch at kernel start, 2 = after the layers
   double p, q, R, z;   // z = RN(1/R)
   double S0, sgn, nE;  // payoff(S) = max(fma(sgn, S, nE), 0) = max(cp*(S - E), 0)
 };
@@ -66,13 +67,12 @@ __global__ void __launch_bounds__(kTreeWarps * 32) tree_steps_kernel(TreeArgs a)
   const long long n_out = a.n0 - a.steps;
   if (base > n_out) return;  // warps are independent: no block-level barrier below
   const long long i0 = base + (long long)lane * kR;
+  // Programmatic dependent launch: let the next launch of the chain be scheduled now (its CTAs park in
+  // griddepcontrol.wait), stage everything that does not depend on the previous launch, then wait for the previous
+  // launch's layer to be complete and visible. Without the launch attribute both instructions are no-ops.
+  if (a.trig == 1) asm volatile("griddepcontrol.launch_dependents;");
 
   double v[kR], A[kR], W[kR];
-#pragma unroll
-  for (int j = 0; j < kR; ++j) {
-    const long long i = i0 + j;
-    v[j] = (i <= a.n0) ? a.vin[i] : 0.0;
-  }
   // d-power window: entry k holds pd[lo + k], lo = n0 - kSteps - base - kL + 1 (clamped reads below 0 are never used
   // by a node inside the tree); padded index k + (k >> 3) makes the lane stride 9 doubles (conflict-free LDS.64)
   double* my_pd = s_pd + (kAmer ? warp * kPad : 0);
@@ -88,6 +88,12 @@ __global__ void __launch_bounds__(kTreeWarps * 32) tree_steps_kernel(TreeArgs a)
       my_pd[k + (k >> 3)] = (idx >= 0 && idx <= a.n0) ? a.pd[idx] : 0.0;
     }
     __syncwarp();
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < kR; ++j) {
+    const long long i = i0 + j;
+    v[j] = (i <= a.n0) ? a.vin[i] : 0.0;
   }
   // node (i0 + j) of the layer reached after s+1 steps (n = n0 - 1 - s) needs pd[n - i0 - j] = window entry
   // k(s, j) = kSteps + kL - 2 - lane*kR - (s + j): it depends on s + j only, so the lane keeps entries t = s..s+kR-1 in
@@ -126,6 +132,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) tree_steps_kernel(TreeArgs a)
       }
     }
   }
+  if (a.trig == 2) asm volatile("griddepcontrol.launch_dependents;");
 #pragma unroll
   for (int j = 0; j < kR; ++j) {
     const long long i = i0 + j;
@@ -147,6 +154,16 @@ __global__ void tree_terminal_kernel(double* __restrict__ v, const double* __res
 template <int kR, int kSteps>
 static int tree_launch_all(Ctx& c, TreeArgs a, long long N, bool amer, double* buf0, double* buf1) {
   constexpr int kStride = 32 * kR - kSteps;
+  // PCF_TREE_PDL=0 turns the programmatic dependent launch off (A/B knob); the first launch of the chain follows a
+  // plain kernel, for which the attribute is harmless
+  // Programmatic dependent launch (profiles/r1_notes.md, r1_tune_tree_pdl.log): releasing the next launch AFTER the
+  // layers (mode 2) hides the launch gap -- 11.1 -> 8.0 ms (European) / 20.0 -> 16.8 ms (American) at N = 1e5, 85 -> 62 ms
+  // at N = 4e5. Releasing it at kernel start (mode 1) parks the CTAs of the next launches on the SMs while this one
+  // computes and skews their placement: 2x SLOWER for N >= 1e5. PCF_TREE_PDL = 0 | 1 | 2 overrides.
+  const char* pe = getenv("PCF_TREE_PDL");
+  const int trig = pe ? atoi(pe) : 2;
+  const bool pdl = trig != 0;
+  a.trig = trig;
   long long n = N;
   double* in = buf0;
   double* out = buf1;
@@ -155,8 +172,18 @@ static int tree_launch_all(Ctx& c, TreeArgs a, long long N, bool amer, double* b
     a.vin = in; a.vout = out; a.n0 = n; a.steps = steps;
     const long long warps = (n - steps + 1 + kStride - 1) / kStride;
     const int grid = (int)((warps + kTreeWarps - 1) / kTreeWarps);
-    if (amer) tree_steps_kernel<kR, kSteps, true><<<grid, kTreeWarps * 32, 0, c.stream>>>(a);
-    else tree_steps_kernel<kR, kSteps, false><<<grid, kTreeWarps * 32, 0, c.stream>>>(a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kTreeWarps * 32);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (amer) PCF_CUDA(cudaLaunchKernelEx(&cfg, tree_steps_kernel<kR, kSteps, true>, a));
+    else PCF_CUDA(cudaLaunchKernelEx(&cfg, tree_steps_kernel<kR, kSteps, false>, a));
     c.launches++;
     n -= steps;
     std::swap(in, out);
@@ -213,11 +240,12 @@ int run_binom_tree(Ctx& c, const pcf_params& p, bool american) {
   c.launches++;
   // launch shape: PCF_TREE = <nodes per lane><layers per launch / 8>  (tuning knob)
   const char* e = getenv("PCF_TREE");
-  const int shape = e ? atoi(e) : 48;
+  const int shape = e ? atoi(e) : (N > 250000 ? 44 : 48);  // wide trees: less redundancy (1.33x) beats fewer launches
   switch (shape) {
     case 22: return tree_launch_all<2, 16>(c, a, N, american, buf0, buf1);
     case 44: return tree_launch_all<4, 32>(c, a, N, american, buf0, buf1);
     case 48: return tree_launch_all<4, 64>(c, a, N, american, buf0, buf1);
+    case 68: return tree_launch_all<6, 64>(c, a, N, american, buf0, buf1);
     case 88: return tree_launch_all<8, 64>(c, a, N, american, buf0, buf1);
     case 84: return tree_launch_all<8, 32>(c, a, N, american, buf0, buf1);
     default:

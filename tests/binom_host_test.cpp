@@ -22,7 +22,18 @@ int main(int argc, char** argv) {
     fill_binom_args(S0, E, r, sigma, Tm, N, cp, a);
     long long until = (N % 2 != 0) ? (N + 1) / 2 : N / 2;
     long double sum = end_terms(a, tv);
-    for (long long i = 1; i < until; ++i) sum += pair_terms(i, a, tv, hc);
+    // the screening pass (pair_dead) may only settle pairs that pair_terms evaluates to exactly 0.0
+    long long dead = 0, wrong = 0;
+    for (long long i = 1; i < until; ++i) {
+      const double t = pair_terms(i, a, tv, hc);
+      if (pair_dead((double)i, (double)(N - i), a, tv, hc)) {
+        ++dead;
+        if (t != 0.0) ++wrong;
+      }
+      sum += t;
+    }
+    if (wrong) { std::printf("SCREEN VIOLATION %lld of %lld\n", wrong, dead); return 1; }
+    std::fprintf(stderr, "N=%lld screened %lld of %lld pairs\n", N, dead, until - 1);
     if (N % 2 == 0) sum += 0.5 * pair_terms(N / 2, a, tv, hc);
     std::printf("%.17g\n", (double)(expl(-(long double)r * Tm) * sum));
   }

@@ -277,6 +277,15 @@ def test_binom_matches_exact_sum(gpu, golden):
         assert rel(gw.price, g.price) < 1e-14
 
 
+def test_binom_screening_pass_is_bit_identical(gpu):
+    # the two-logarithm screen (binom_math.cuh pair_dead) only settles pairs the full routine evaluates to exactly 0.0
+    for P, pf in ((P1, "call"), (P1, "put"), ((100, 110, 0.02, 0.75, 1), "call"), ((50, 60, 0.1, 0.9, 2.5), "put")):
+        for N in (1, 2, 3, 10, 101, 1000, 4097, 100_000, 1_000_003, 30_000_000):
+            a = gpu.binom(*P, N, pf)
+            b = gpu.binom(*P, N, pf, screen=False)
+            assert a.sum == b.sum and a.units == b.units == N + 1, (P, pf, N, a.sum, b.sum)
+
+
 def test_binom_full_size_properties(gpu, golden):
     # BASELINE config 2 sizes (N = 1e5 .. 1e8, and the int limit): no NaN where the reference overflows
     # (SURVEY F3); exact agreement with the 50-digit sum on the reference's own lattice doubles; put-call
