@@ -160,6 +160,48 @@ def cpu_reference_asia(n_paths, threads, seed=SEED0):
     return n_paths * M / sec, "port", sec
 
 
+def cpu_reference_other(name, threads):
+    """cpu_baseline of the `others` entries (SURVEY 8d sizes, reduced so that each run takes a few seconds): the
+    reference's own program from oracle/_ref on `threads` host threads, its T_calculation clock; the basket, which the
+    reference cannot build here (Eigen/Boost absent), is the oracle restatement with the reference's OpenMP placement."""
+    import oracle
+    a = (100, 100, 0.05, 0.2, 1)
+    try:
+        if name == "mc_eur_multi":
+            n = 2_000_000
+            _, sec = oracle.mc_basket_omp_timed(*a, n, "call", 16, 0.5, SEED0, threads)
+            return {"value": n / sec, "unit": "path-steps/s", "cores": threads, "kind": "port",
+                    "sample": f"{n} of 1e9 paths, d=16, {sec:.1f} s, oracle restatement with the OpenMP placement of "
+                              "src/mc_eur_multi_omp.cpp:31-46 (serial sample generation)"}
+        if not oracle.have_ref():
+            return None
+        if name == "mc_eur":
+            n = 400_000_000
+            sec = float(oracle.ref_row("mc_eur_omp", "call", *a, n, threads)[12])
+            return {"value": n / sec, "unit": "path-steps/s", "cores": threads, "kind": "reference",
+                    "sample": f"{n} of 2e9 paths, {sec:.1f} s, mc_eur_omp (unmodified reference source, -O2)"}
+        if name == "mc_amer":
+            n, M = 2_000_000, 50
+            sec = float(oracle.ref_row("mc_amer_omp", "put", *a, n, M, threads)[12])
+            return {"value": n * M / sec, "unit": "path-steps/s", "cores": threads, "kind": "reference",
+                    "sample": f"{n} of 1e8 paths x {M} dates, {sec:.1f} s, mc_amer_omp (unmodified reference source, -O2)"}
+        if name in ("binom_embar", "binom_embar_noscreen"):
+            n = 50_000
+            sec = float(oracle.ref_row("binom_embar_omp", "call", *a, n, threads)[12])
+            return {"value": (n + 1) / sec, "unit": "terms/s", "cores": threads, "kind": "reference",
+                    "sample": f"N={n} (the reference's comb() makes the sum O(N^2): terms/s falls as 1/N; N=1e8 is out of "
+                              f"its reach), {sec:.1f} s, binom_embar_omp (unmodified reference source, -O2)"}
+        if name == "binom_vanilla_amer":
+            n = 20_000
+            sec = float(oracle.ref_row("binom_vanilla_amer", "put", *a, n)[12])
+            return {"value": n * (n + 1) / 2 / sec, "unit": "node-updates/s", "cores": 1, "kind": "reference",
+                    "sample": f"N={n} of 1e5 layers, {sec:.1f} s, binom_vanilla_amer (unmodified reference source, -O2; the "
+                              "reference has no parallel flavour of the tree)"}
+    except Exception as ex:  # a missing binary must not take the GPU numbers down with it
+        return {"error": str(ex)}
+    return None
+
+
 def bench_reference(args, rank):
     """--impl reference: rank 0 alone times the reference's CPU path; other ranks exit 0 without work."""
     if rank != 0:
@@ -295,6 +337,8 @@ def main():
                                "e2e": mo["units"] * 2 / mo["wall_s"], "ms_per_step": 1e3 * mo["device_s"] / 2,
                                "price": mo["price"], "std_error": mo["se"], "gpu_launches": mo["launches"],
                                "roofline": roofline_for(other, ups / n_gpus, fp64_peak, hbm, hbm_src)})
+                if job.rank == 0 and n_gpus == 1 and not args.no_cpu:
+                    others[-1]["cpu_baseline"] = cpu_reference_other(other, host_threads())
             except Exception as ex:  # e.g. the path store does not fit
                 others.append({"workload": WORKLOADS[other]["config"], "error": str(ex)})
 

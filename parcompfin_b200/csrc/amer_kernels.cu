@@ -246,6 +246,8 @@ struct SweepArgs {
   long long Np;         // multiple of 16
   double E;
   int cp, m, M;
+  int rev;              // tiles are walked from the far end (alternate dates: the tail of the previous kernel's
+                        // row m-1 and date tiles is still in L2 when this kernel starts there)
   int first;            // date M: no decision
   int lsm;              // PCF_FLAG_AMER_LSM
   int stages;
@@ -335,19 +337,24 @@ __global__ void __launch_bounds__(kSweepBlock, kCtas) amer_sweep_kernel(SweepArg
   if (tid >= kSweepConsumers) {
     // ---- producer warp: one elected lane keeps the ring full; it starts before the moments of date m arrive
     if (tid == kSweepConsumers) {
-      uint64_t pol;
+      // row m is dead after this kernel (evict-first); row m-1 and the dates are read again by the next kernel, which
+      // starts where this one ends (a.rev alternates), so they keep the default policy
+      uint64_t pol, pol_keep;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+      if (a.dbg & 32) pol_keep = pol;
       int s = 0;
       uint32_t ph = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (long long tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
+        const long long t = a.rev ? ntiles - 1 - tt : tt;
         mbar_wait(&s_empty[s], ph ^ 1);
         const long long c0 = t * kTilePaths;
         const uint32_t n = (uint32_t)((Np - c0 < kTilePaths) ? (Np - c0) : kTilePaths);  // multiple of 16
         unsigned char* st = ring + (size_t)s * kStage;
         mbar_arrive_expect_tx(&s_full[s], n * (uint32_t)(8 + (kMoments ? 8 : 0) + sizeof(WT)));
         bulk_g2s(st, row_m + c0, n * 8u, &s_full[s], pol);
-        if (kMoments) bulk_g2s(st + kTilePaths * 8, row_p + c0, n * 8u, &s_full[s], pol);
-        bulk_g2s(st + kTilePaths * 16, when + c0, n * (uint32_t)sizeof(WT), &s_full[s], pol);
+        if (kMoments) bulk_g2s(st + kTilePaths * 8, row_p + c0, n * 8u, &s_full[s], pol_keep);
+        bulk_g2s(st + kTilePaths * 16, when + c0, n * (uint32_t)sizeof(WT), &s_full[s], pol_keep);
         if (++s == a.stages) { s = 0; ph ^= 1; }
       }
     }
@@ -425,7 +432,8 @@ __global__ void __launch_bounds__(kSweepBlock, kCtas) amer_sweep_kernel(SweepArg
 
     int s = 0;
     uint32_t ph = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (long long tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
+      const long long t = a.rev ? ntiles - 1 - tt : tt;
       const unsigned char* st = ring + (size_t)s * kStage;
       const long long c0t = t * kTilePaths;
       const bool live = c0t + 4 * tid < Np;  // Np is a multiple of 16: a quad is live or dead as a whole
@@ -704,6 +712,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   for (int m = M; m >= 1; --m) {
     sa.m = m;
     sa.first = (m == M);
+    sa.rev = (sa.dbg & 32) ? 0 : ((M - m) & 1);
     sa.mom_in = mom[m & 1];
     if (m < M && !use_peer(c)) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));
     const PeerLink l_out = next_link(c);
