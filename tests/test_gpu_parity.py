@@ -371,6 +371,40 @@ def test_determinism_and_homogeneity(gpu):
     assert e1.price == e2.price
 
 
+def test_full_size_properties(gpu, golden):
+    """BASELINE.json's sizes (configs 3, 4, 5 and the 2e9-path European run of the roofline figure), where the oracle
+    cannot follow: size-independent properties instead -- exact homogeneity, run-to-run bit equality, closed forms
+    within 3 standard errors, agreement with the smaller runs that ARE pinned against the reference."""
+    # config 3: 1e9 paths x 252 dates. Scaling (S0, E) by 2 is exact in binary FP: every path doubles bit for bit.
+    a = gpu.mc_asia(*P1, 1_000_000_000, 252, "call", seed=20240229)
+    b = gpu.mc_asia(200, 200, 0.05, 0.2, 1, 1_000_000_000, 252, "call", seed=20240229)
+    assert a.n == 10 ** 9 and a.units == 252 * 10 ** 9
+    assert rel(b.sum, 2 * a.sum) < 1e-14 and rel(b.sumsq, 4 * a.sumsq) < 1e-14
+    print("homogeneity at 1e9 paths: exact" if (b.sum == 2 * a.sum and b.sumsq == 4 * a.sumsq) else "homogeneity: 1e-14")
+    small = gpu.mc_asia(*P1, 4_000_000, 252, "call", seed=3)      # pinned against the reference's run above
+    assert abs(a.price - small.price) < 3 * math.hypot(a.std_error, small.std_error)
+    assert a.std_error < small.std_error / 15                       # 250x the paths: error bar shrinks ~15.8x
+    # the European roofline run: 2e9 paths against Black-Scholes (standard error ~3.3e-4)
+    e = gpu.mc_eur(*P1, 2_000_000_000, "call", seed=20240229)
+    assert abs(e.price - BS_CALL) < 3 * e.std_error and e.std_error < 4e-4
+    # config 4: d = 16, 1e9 paths; rho -> 1 collapses the basket to one asset => Black-Scholes
+    g = gpu.mc_eur_multi(*P1, 1_000_000_000, "call", 16, 1 - 1e-12, seed=4)
+    assert abs(g.price - BS_CALL) < 3 * g.std_error and g.std_error < 6e-4
+    g1 = gpu.mc_eur_multi(*P1, 1_000_000_000, "call", 16, 0.5, seed=20240229)
+    g2 = gpu.mc_eur_multi(*P1, 20_000_000, "call", 16, 0.5, seed=5)
+    assert abs(g1.price - g2.price) < 3 * math.hypot(g1.std_error, g2.std_error)
+    assert g1.price < BS_CALL                                       # diversification lowers the basket's volatility
+    # config 5: 1e8 paths x 50 dates (40 GB path store): bit-reproducible, floored at immediate exercise, and within
+    # the error bars of the 4e6-path run that is pinned against the reference's own 1e6-path result
+    x = gpu.mc_amer(*P1, 100_000_000, 50, "put", seed=20240229)
+    y = gpu.mc_amer(*P1, 100_000_000, 50, "put", seed=20240229)
+    assert x.price == y.price and x.sumsq == y.sumsq and x.units == 50 * 10 ** 8
+    z = gpu.mc_amer(*P1, 4_000_000, 50, "put", seed=3)
+    assert abs(x.price - z.price) < 3 * math.hypot(x.std_error, z.std_error)
+    ref = [c for c in golden["reference_vectors"]["mc_amer"] if c["N"] == 1_000_000][0]
+    assert abs(x.price - ref["price"]) < 3 * z.std_error * 2        # reference run: 1e6 paths, error bar 2x z's
+
+
 def test_put_call_parity_same_stream(gpu):
     N = 5_000_000
     c = gpu.mc_eur(*P1, N, "call", seed=21)
