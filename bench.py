@@ -50,7 +50,7 @@ WORKLOADS = {
                          kernel="mc_basket_kernel", assets=16, rho=0.5),
     "mc_amer": dict(config="mc_amer put, 1e8 paths x 50 exercise dates, paths in HBM (BASELINE config 5)",
                     N=100_000_000, M=50, steps_per_unit=50, bytes=36.0, bound="hbm", unit="path-steps/s",
-                    kernel="amer_paths_kernel+amer_sweep_kernel"),
+                    kernel="amer_sweep_kernel+amer_paths_kernel"),
     "binom_embar": dict(config="binom_embar call 100/100/.05/.2/1, N=1e8 steps (BASELINE config 2)",
                         N=100_000_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
                         kernel="binom_terms_kernel"),
@@ -255,7 +255,35 @@ def measure(pcf, dist, job, name, steps, warmup, N=None):
                 price=last.price, se=last.std_error, t0=t0)
 
 
+def ncu_traffic(kernel_names):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu launch list of this very command
+    (profiles/ncu_traffic.json, written by tools/summarize_launches.py); None when no capture is committed. For a
+    workload made of several kernels the figure is per launch of the DOMINANT one (most DRAM bytes)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        ks = json.load(open(path))["kernels"]
+    except (ValueError, KeyError):
+        return None
+    best = None
+    for frag in kernel_names.split("+"):
+        for k, v in ks.items():
+            if k.startswith(frag):
+                if best is None or v["dram_bytes_per_launch"] > best:
+                    best = v["dram_bytes_per_launch"]
+    return best
+
+
 def roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src):
+    r = _roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src)
+    r["traffic"] = ncu_traffic(WORKLOADS[name]["kernel"])
+    if r["traffic"] is not None:
+        r["traffic_source"] = "profiles/ncu_traffic.json: DRAM read+write bytes per launch of the dominant kernel (ncu)"
+    return r
+
+
+def _roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src):
     w = WORKLOADS[name]
     if w["bound"] == "fp64":
         ach = units_per_s * w["slots"] * 2 / 1e12
