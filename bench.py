@@ -47,7 +47,7 @@ WORKLOADS = {
                    kernel="mc_eur_kernel"),
     "mc_eur_multi": dict(config="mc_eur_multi call, d=16 rho=0.5, 1e9 paths (BASELINE config 4)",
                          N=1_000_000_000, M=0, steps_per_unit=1, slots=990.0, bound="fp64", unit="path-steps/s",
-                         kernel="mc_basket_kernel", assets=16, rho=0.5),
+                         kernel="mc_basket_equi_kernel", assets=16, rho=0.5),
     "mc_amer": dict(config="mc_amer put, 1e8 paths x 50 exercise dates, paths in HBM (BASELINE config 5)",
                     N=100_000_000, M=50, steps_per_unit=50, bytes=36.0, bound="hbm", unit="path-steps/s",
                     kernel="amer_sweep_kernel+amer_paths_kernel"),
