@@ -66,7 +66,7 @@ WORKLOADS = {
                                       "needs ~45 s per tree at this size)",
                                N=100_000, M=0, steps_per_unit=1, slots=18.0, bound="fp64", unit="node-updates/s",
                                algo_src="DESIGN 4.5: 2 mul + add + IEEE division 10 + 2 mul + payoff 2 + max 1",
-                               kernel="tree_steps_kernel"),
+                               kernel="tree_steps_kernel", replicas=True),
 }
 
 
@@ -364,7 +364,9 @@ def main():
                 others.append({"workload": WORKLOADS[other]["config"], "value": ups, "unit": WORKLOADS[other]["unit"],
                                "e2e": mo["units"] * 2 / mo["wall_s"], "ms_per_step": 1e3 * mo["device_s"] / 2,
                                "price": mo["price"], "std_error": mo["se"], "gpu_launches": mo["launches"],
-                               "roofline": roofline_for(other, ups / n_gpus, fp64_peak, hbm, hbm_src)})
+                               # a path that does not shard (the tree) runs as replicas: its rate is per GPU already
+                               "roofline": roofline_for(other, ups if WORKLOADS[other].get("replicas") else ups / n_gpus,
+                                                        fp64_peak, hbm, hbm_src)})
                 if job.rank == 0 and n_gpus == 1 and not args.no_cpu:
                     others[-1]["cpu_baseline"] = cpu_reference_other(other, host_threads())
             except Exception as ex:  # e.g. the path store does not fit
