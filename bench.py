@@ -48,6 +48,11 @@ WORKLOADS = {
     "mc_eur_multi": dict(config="mc_eur_multi call, d=16 rho=0.5, 1e9 paths (BASELINE config 4)",
                          N=1_000_000_000, M=0, steps_per_unit=1, slots=990.0, bound="fp64", unit="path-steps/s",
                          kernel="mc_basket_equi_kernel", assets=16, rho=0.5),
+    # SURVEY 8(f).4 (widening row): per-asset spots/vols/weights and a dense SPD covariance (no equicorrelation shortcut)
+    "mc_basket_general": dict(config="mc_basket call, d=16, per-asset S0/sigma/weights, dense SPD covariance, 1e9 paths "
+                                     "(SURVEY 8f.4: the general kernel, full triangular factor)",
+                              N=1_000_000_000, M=0, steps_per_unit=1, slots=990.0, bound="fp64", unit="path-steps/s",
+                              kernel="mc_basket_kernel", assets=16),
     "mc_amer": dict(config="mc_amer put, 1e8 paths x 50 exercise dates, paths in HBM (BASELINE config 5)",
                     N=100_000_000, M=50, steps_per_unit=50, bytes=36.0, bound="hbm", unit="path-steps/s",
                     kernel="amer_sweep_kernel+amer_paths_kernel"),
@@ -80,6 +85,14 @@ def run_ours_once(pcf, name, seed, N=None):
         return pcf.mc_eur(*a, N, "call", seed=seed)
     if name == "mc_eur_multi":
         return pcf.mc_eur_multi(*a, N, "call", w["assets"], w["rho"], seed=seed)
+    if name == "mc_basket_general":
+        import numpy as np
+        rng = np.random.default_rng(16)
+        d = w["assets"]
+        B = rng.standard_normal((d, d))
+        cov = B @ B.T / d + 0.2 * np.eye(d)
+        return pcf.mc_basket(rng.uniform(80, 120, d), P["E"], P["r"], rng.uniform(.1, .4, d), P["T"], N, "call", d,
+                             weights=rng.dirichlet(np.ones(d)), cov=cov, seed=seed)
     if name == "mc_amer":
         return pcf.mc_amer(*a, N, w["M"], "put", seed=seed)
     if name == "binom_embar":

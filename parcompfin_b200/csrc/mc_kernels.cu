@@ -277,10 +277,38 @@ int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay
 // L (row-major, lower) sits in constant memory: every lane reads the same L[a][k] at the same
 // time, which is the constant cache's broadcast case.
 __constant__ double c_L[PCF_MAX_ASSETS * PCF_MAX_ASSETS];
-// per-asset parameters of the general kernel; the reference's basket has one sigma, S0 and weight 1/d
-__constant__ double c_bsig[PCF_MAX_ASSETS];    // sigma_a
-__constant__ double c_bdrift[PCF_MAX_ASSETS];  // (r - sigma_a^2/2) T
-__constant__ double c_bw[PCF_MAX_ASSETS];      // w_a * S0_a
+// General kernel: per-asset parameters are folded into the constants on the host so that every FMA of the kernel has at
+// most ONE constant operand (a DFMA takes one c[bank][offset]; a second one costs an LDC and its scoreboard wait):
+//   c_L[a][k]  = sigma_a * A[a][k]                      -> bt[a] = sigma_a * (A z)_a
+//   c_bw[a]    = w_a * S0_a * exp((r - sigma_a^2/2) T)  -> basket = sum_a c_bw[a] * exp(bt[a])     (mc_eur_multi.cpp:30)
+// The reference's basket has one sigma, one S0 and weight 1/d (spec == nullptr in run_mc_basket).
+__constant__ double c_bw[PCF_MAX_ASSETS];
+
+// Keeps a loop-invariant value in a register: without this ptxas rematerialises the hoisted polynomial coefficients
+// as constant loads inside the loop (341 LDC per path in the d = 16 kernel, ADU pipe 38 % busy).
+__device__ __forceinline__ double pin_reg(double v) {
+  asm volatile("" : "+d"(v));
+  return v;
+}
+
+// exp_table() with its two two-constant FMAs fed from pinned registers
+__device__ __forceinline__ double exp_table_pinned(double x, const TableView& tv, double magic, double e5) {
+  const double t = fma(x, 46.16624130844683, magic);
+  const double kf = t - magic;
+  double r = fma(kf, -0.02166084939249829, x);
+  r = fma(kf, -7.247021293269686e-19, r);
+  const uint32_t n = (uint32_t)__double2loint(t);
+  const double T = tv.exp_tab[(n & 31u) * tv.stride8];
+  double q = fma(r, 1.0 / 720.0, e5);
+  q = fma(q, r, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  const double rq = r * q;
+  const double v = fma(T, rq, T);
+  const int k = (int)n >> 5;
+  return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+}
 
 struct BasketArgs {
   double E, drift, sigma;  // drift = (r - sigma^2/2) T   (no sqrt(T) anywhere: SURVEY F9)
@@ -291,9 +319,11 @@ struct BasketArgs {
   const double* Z;  // replay: Z[(n-n0)*d + a]
 };
 
-// kFull: the normal transform is a full matrix (eigen-decomposition fallback of mvn.h:72-76), not a lower triangle
-template <int D, bool kReplay, bool kFull>
-__global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const MathTables* __restrict__ tables,
+// kFull: the normal transform is a full matrix (eigen-decomposition fallback of mvn.h:72-76), not a lower triangle.
+// kPaths paths per thread iteration: their Philox / Box-Muller chains are independent instruction streams in one loop
+// body, which is what keeps the FP64 pipe fed with one CTA per SM (same finding as mc_asia_kernel, profiles/r1_notes.md).
+template <int D, bool kReplay, bool kFull, int kPaths, int kMinB>
+__global__ void __launch_bounds__(kBlock, kMinB) mc_basket_kernel(BasketArgs a, const MathTables* __restrict__ tables,
                                                            PeerLink link, double* partials, unsigned int* ticket,
                                                            double* out) {
   __shared__ double smem[2 * 2 * 32];
@@ -301,41 +331,60 @@ __global__ void __launch_bounds__(kBlock) mc_basket_kernel(BasketArgs a, const M
   const TableView tv = stage_tables(tables, tab_smem);
   Hoisted hc;
   hc.load();
+  const double xmagic = 6755399441055744.0, xe5 = 1.0 / 120.0;
   const PhiloxKey key(a.seed);
   Comp s1, s2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long n = a.n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < a.n1; n += stride) {
-    double bt[D];
+  for (long long nb = a.n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; nb < a.n1; nb += stride * kPaths) {
+    double bt[kPaths][D];
+    long long nq[kPaths];
 #pragma unroll
-    for (int i = 0; i < D; ++i) bt[i] = 0.0;
+    for (int q = 0; q < kPaths; ++q) {
+      nq[q] = (nb + q * stride < a.n1) ? nb + q * stride : nb;  // clamp: a dead slot recomputes path nb, result dropped
+#pragma unroll
+      for (int i = 0; i < D; ++i) bt[q][i] = 0.0;
+    }
     // column sweep of the triangular product: z_k is consumed as soon as it is drawn
 #pragma unroll
     for (int j = 0; j < D / 2 + (D & 1); ++j) {
       if (2 * j < a.d) {
-        double z0, z1;
-        if (kReplay) {
-          const double* z = a.Z + (n - a.n0) * (long long)a.d;
-          z0 = z[2 * j];
-          z1 = (2 * j + 1 < a.d) ? z[2 * j + 1] : 0.0;
-        } else {
-          normal_pair(key, (uint64_t)n, (uint32_t)j, PCF_STREAM_BASKET, tv, hc, z0, z1);
+        double z0[kPaths], z1[kPaths];
+#pragma unroll
+        for (int q = 0; q < kPaths; ++q) {
+          if (kReplay) {
+            const double* z = a.Z + (nq[q] - a.n0) * (long long)a.d;
+            z0[q] = z[2 * j];
+            z1[q] = (2 * j + 1 < a.d) ? z[2 * j + 1] : 0.0;
+          } else {
+            normal_pair(key, (uint64_t)nq[q], (uint32_t)j, PCF_STREAM_BASKET, tv, hc, z0[q], z1[q]);
+          }
         }
 #pragma unroll
-        for (int i = kFull ? 0 : 2 * j; i < D; ++i) bt[i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j], z0, bt[i]);
-        if (2 * j + 1 < D) {
+        for (int q = 0; q < kPaths; ++q) {
 #pragma unroll
-          for (int i = kFull ? 0 : 2 * j + 1; i < D; ++i)
-            bt[i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j + 1], z1, bt[i]);
+          for (int i = kFull ? 0 : 2 * j; i < D; ++i) bt[q][i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j], z0[q], bt[q][i]);
+          if (2 * j + 1 < D) {
+#pragma unroll
+            for (int i = kFull ? 0 : 2 * j + 1; i < D; ++i)
+              bt[q][i] = fma(c_L[i * PCF_MAX_ASSETS + 2 * j + 1], z1[q], bt[q][i]);
+          }
         }
       }
     }
-    double basket = 0.0;
+    double t1 = 0.0, t2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < D; ++i)
-      if (i < a.d) basket = fma(c_bw[i], exp_table(fma(c_bsig[i], bt[i], c_bdrift[i]), tv), basket);  // :30
-    double v = payoff(basket, a.E, a.cp);
-    s1.add(v);
-    s2.add(v * v);
+    for (int q = 0; q < kPaths; ++q) {
+      double basket = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+        if (i < a.d) basket = fma(c_bw[i], exp_table_pinned(bt[q][i], tv, xmagic, xe5), basket);  // :30
+      double v = payoff(basket, a.E, a.cp);
+      if (kPaths > 1 && nb + q * stride >= a.n1) v = 0.0;
+      t1 += v;
+      t2 = fma(v, v, t2);
+    }
+    s1.add(t1);
+    s2.add(t2);
   }
   Comp v[2] = {s1, s2};
   grid_reduce<2>(v, smem, partials, ticket, out, &link);
@@ -407,12 +456,36 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) mc_basket_equi_kernel(Bask
   grid_reduce<2>(v, smem, partials, ticket, out, &link);
 }
 
+// Grid = one wave of resident CTAs (the kernel's own occupancy, not an assumed one).
+template <typename K>
+static int basket_launch(Ctx& c, K kernel, const BasketArgs& a, long long paths, int per_thread, const PeerLink& link) {
+  int per_sm = 0;
+  PCF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, kTableSmemBytes));
+  const int grid = grid_for(c, (paths + per_thread - 1) / per_thread, kBlock, per_sm > 0 ? per_sm : 1);
+  kernel<<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+  return PCF_OK;
+}
+
+// Launch shape of the native kernel: PCF_BASKET_GEN = <paths per thread><CTAs per SM> (tuning knob): 13 (default) | 21.
+// Measured at d = 16, 1e9 paths (profiles/r1_notes.md): 13 -> 82 ms, 22 -> 88 ms, 41 -> 92 ms, 21 -> 102 ms: unlike the
+// Asian and equicorrelation kernels this one prefers warps to paths per thread (its 136 factor entries are used once per
+// path and already crowd the uniform register file). The replay flavour (parity path) is built once.
 template <int D>
-static void launch_basket(Ctx& c, const BasketArgs& a, int grid, bool replay, bool full, const PeerLink& link) {
-#define PCF_BK(R, F) mc_basket_kernel<D, R, F><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out)
-  if (replay) { if (full) PCF_BK(true, true); else PCF_BK(true, false); }
-  else { if (full) PCF_BK(false, true); else PCF_BK(false, false); }
-#undef PCF_BK
+static int launch_basket(Ctx& c, const BasketArgs& a, long long paths, bool replay, bool full, const PeerLink& link) {
+  if (replay) return full ? basket_launch(c, mc_basket_kernel<D, true, true, 1, 3>, a, paths, 1, link)
+                          : basket_launch(c, mc_basket_kernel<D, true, false, 1, 3>, a, paths, 1, link);
+  const char* e = getenv("PCF_BASKET_GEN");
+  const int shape = e ? atoi(e) : 13;
+#define PCF_BG(P, B) (full ? basket_launch(c, mc_basket_kernel<D, false, true, P, B>, a, paths, P, link) \
+                           : basket_launch(c, mc_basket_kernel<D, false, false, P, B>, a, paths, P, link))
+  switch (shape) {
+    case 13: return PCF_BG(1, 3);
+    case 21: return PCF_BG(2, 1);
+    default:
+      set_last_error("unknown PCF_BASKET_GEN");
+      return PCF_EINVAL;
+  }
+#undef PCF_BG
 }
 
 // `spec` == nullptr: the reference's basket (one sigma, one S0, weights 1/d). Otherwise per-asset arrays of length d and
@@ -421,22 +494,21 @@ int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-m
                   Shard paths, const double* d_replay, const PeerLink& link, const BasketHost* spec) {
   const int d = p.assets;
   const bool full = spec && spec->full;
-  double Lpad[PCF_MAX_ASSETS * PCF_MAX_ASSETS] = {0};
-  for (int i = 0; i < d; ++i)
-    for (int k = 0; k < (full ? d : i + 1); ++k) Lpad[i * PCF_MAX_ASSETS + k] = L_host[i * d + k];
+  double Lfold[PCF_MAX_ASSETS * PCF_MAX_ASSETS] = {0};  // sigma_a folded into row a (general kernel)
   {
-    double sg[PCF_MAX_ASSETS] = {0}, dr[PCF_MAX_ASSETS] = {0}, w[PCF_MAX_ASSETS] = {0};
+    double w[PCF_MAX_ASSETS] = {0};
     for (int i = 0; i < d; ++i) {
       const double s_i = spec ? spec->sigma[i] : p.sigma;
-      sg[i] = s_i;
-      dr[i] = (p.r - s_i * s_i / 2) * p.T;
-      w[i] = spec ? spec->weight[i] * spec->S0[i] : (1.0 / (double)d) * p.S0;
+      for (int k = 0; k < (full ? d : i + 1); ++k) {
+        Lfold[i * PCF_MAX_ASSETS + k] = s_i * L_host[i * d + k];
+      }
+      const long double drift = ((long double)p.r - (long double)s_i * s_i / 2) * (long double)p.T;
+      const long double ws0 = spec ? (long double)spec->weight[i] * spec->S0[i] : (long double)p.S0 / d;
+      w[i] = (double)(ws0 * expl(drift));
     }
-    PCF_CUDA(cudaMemcpyToSymbolAsync(c_bsig, sg, sizeof(sg), 0, cudaMemcpyHostToDevice, c.stream));
-    PCF_CUDA(cudaMemcpyToSymbolAsync(c_bdrift, dr, sizeof(dr), 0, cudaMemcpyHostToDevice, c.stream));
     PCF_CUDA(cudaMemcpyToSymbolAsync(c_bw, w, sizeof(w), 0, cudaMemcpyHostToDevice, c.stream));
   }
-  PCF_CUDA(cudaMemcpyToSymbolAsync(c_L, Lpad, sizeof(Lpad), 0, cudaMemcpyHostToDevice, c.stream));
+  PCF_CUDA(cudaMemcpyToSymbolAsync(c_L, Lfold, sizeof(Lfold), 0, cudaMemcpyHostToDevice, c.stream));
   BasketArgs a;
   a.E = p.E; a.sigma = p.sigma; a.cp = p.cp; a.d = d;
   a.drift = (p.r - p.sigma * p.sigma / 2) * p.T;
@@ -483,12 +555,12 @@ int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-m
     PCF_CUDA(cudaGetLastError());
     return PCF_OK;
   }
-  int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
-  if (d <= 2) launch_basket<2>(c, a, grid, rp, full, link);
-  else if (d <= 4) launch_basket<4>(c, a, grid, rp, full, link);
-  else if (d <= 8) launch_basket<8>(c, a, grid, rp, full, link);
-  else if (d <= 16) launch_basket<16>(c, a, grid, rp, full, link);
-  else launch_basket<32>(c, a, grid, rp, full, link);
+  const long long np = paths.size();
+  if (d <= 2) PCF_TRY(launch_basket<2>(c, a, np, rp, full, link));
+  else if (d <= 4) PCF_TRY(launch_basket<4>(c, a, np, rp, full, link));
+  else if (d <= 8) PCF_TRY(launch_basket<8>(c, a, np, rp, full, link));
+  else if (d <= 16) PCF_TRY(launch_basket<16>(c, a, np, rp, full, link));
+  else PCF_TRY(launch_basket<32>(c, a, np, rp, full, link));
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;

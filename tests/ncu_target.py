@@ -11,6 +11,12 @@ for i in range(reps):
     if name == "mc_asia": r = pcf.mc_asia(*a, N, 252, "call", seed=i)
     elif name == "mc_eur": r = pcf.mc_eur(*a, N, "call", seed=i)
     elif name == "mc_eur_multi": r = pcf.mc_eur_multi(*a, N, "call", 16, .5, seed=i)
+    elif name == "mc_basket_general":
+        import numpy as np
+        rng = np.random.default_rng(16)
+        B = rng.standard_normal((16, 16))
+        r = pcf.mc_basket(rng.uniform(80, 120, 16), 100., .05, rng.uniform(.1, .4, 16), 1., N, "call", 16,
+                          weights=rng.dirichlet(np.ones(16)), cov=B @ B.T / 16 + .2 * np.eye(16), seed=i)
     elif name == "mc_amer": r = pcf.mc_amer(*a, N, 50, "put", seed=i)
     elif name == "binom_embar": r = pcf.binom(*a, N, "call")
     print(name, N, r.price, r.seconds_kernel, r.units / r.seconds_kernel)
