@@ -40,11 +40,13 @@ SEED0 = 20240229
 WORKLOADS = {
     "mc_asia": dict(config="mc_asia call 100/100/.05/.2/1, 1e9 paths x 252 dates (BASELINE config 3)",
                     N=1_000_000_000, M=252, steps_per_unit=252, slots=55.0, bound="fp64", unit="path-steps/s",
-                    kernel="mc_asia_kernel"),
+                    kernel="mc_asia_kernel", exec_cycles=97.0,
+                    exec_src="SASS of the shipped loop (tests/sass_count.py): 31.5 FP64 + 8.5 IMAD.WIDE per path-step"),
     "mc_eur": dict(config="mc_eur call 100/100/.05/.2/1, 2e9 paths (config 1 at the size SURVEY 8d quotes the "
                           "roofline on; 1e7 paths is 30 us of work)",
                    N=2_000_000_000, M=0, steps_per_unit=1, slots=60.0, bound="fp64", unit="path-steps/s",
-                   kernel="mc_eur_kernel"),
+                   kernel="mc_eur_kernel", exec_cycles=106.75,
+                   exec_src="SASS of the shipped loop (tests/sass_count.py): 34.4 FP64 + 9.5 IMAD.WIDE per path"),
     "mc_eur_multi": dict(config="mc_eur_multi call, d=16 rho=0.5, 1e9 paths (BASELINE config 4)",
                          N=1_000_000_000, M=0, steps_per_unit=1, slots=990.0, bound="fp64", unit="path-steps/s",
                          kernel="mc_basket_equi_kernel", assets=16, rho=0.5),
@@ -52,7 +54,8 @@ WORKLOADS = {
     "mc_basket_general": dict(config="mc_basket call, d=16, per-asset S0/sigma/weights, dense SPD covariance, 1e9 paths "
                                      "(SURVEY 8f.4: the general kernel, full triangular factor)",
                               N=1_000_000_000, M=0, steps_per_unit=1, slots=990.0, bound="fp64", unit="path-steps/s",
-                              kernel="mc_basket_kernel", assets=16),
+                              kernel="mc_basket_kernel", assets=16, exec_cycles=1920.0,
+                              exec_src="ncu: 640 FP64 + 160 IMAD.WIDE warp instructions per path"),
     "mc_amer": dict(config="mc_amer put, 1e8 paths x 50 exercise dates, paths in HBM (BASELINE config 5)",
                     N=100_000_000, M=50, steps_per_unit=50, bytes=36.0, bound="hbm", unit="path-steps/s",
                     kernel="amer_sweep_kernel+amer_paths_kernel"),
@@ -290,7 +293,14 @@ def ncu_traffic(kernel_names):
 
 def roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src):
     r = _roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src)
-    r["traffic"] = ncu_traffic(WORKLOADS[name]["kernel"])
+    w = WORKLOADS[name]
+    if "exec_cycles" in w:
+        # The algorithmic slot count (libdevice-based) is above what this build executes, so `frac` can exceed
+        # 1. This is the same rate against the work the kernel actually issues: FP64 instructions take 2 pipe cycles per
+        # warp, IMAD.WIDE (Philox) 4 on the same pipe (tests/ubench); the pipe offers 2 x dfma_peak / 32 cycles per second.
+        r["executed_pipe_frac"] = units_per_s * w["exec_cycles"] / (2.0 * fp64_dfma_per_s)
+        r["executed_work"] = f"{w['exec_cycles']:g} FP64-pipe cycles per warp and unit ({w['exec_src']})"
+    r["traffic"] = ncu_traffic(w["kernel"])
     if r["traffic"] is not None:
         r["traffic_source"] = "profiles/ncu_traffic.json: DRAM read+write bytes per launch of the dominant kernel (ncu)"
     return r
