@@ -85,6 +85,23 @@ def test_normal_transform_is_host_side():
     assert ctypes.sizeof(pcf.PcfBasket) == 40
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/pcf.h compiled as C99 -pedantic by a consumer that links libpcf.so: struct sizes match the ctypes mirror,
+    host-only entry points work, compute before pcf_init() is PCF_ENOINIT, a bad payoff is the reference's message."""
+    import subprocess
+    exe = str(tmp_path / "abi_c_test")
+    libdir = os.path.join(ROOT, "parcompfin_b200")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_c_test.c"), "-o", exe, "-L", libdir, "-lpcf",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.check_output([exe]).decode().splitlines()
+    assert out[0] == f"sizeof {ctypes.sizeof(pcf.PcfParams)} {ctypes.sizeof(pcf.PcfResult)} {ctypes.sizeof(pcf.PcfBasket)} abi 1"
+    assert out[1].startswith("chol 0 ") and abs(float(out[1].split()[2]) - pcf.chol_equicorr(16, 0.5)[15, 15]) < 1e-16
+    assert out[2].startswith("transform 0 0 ") and abs(float(out[2].split()[3]) - 0.75 ** 0.5) < 1e-15
+    assert out[3] == "noinit 12 pcf_init() has not been called"
+    assert out[4] == "badpayoff 1 Unknown payoff function"
+
+
 def test_compute_without_init_or_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():
