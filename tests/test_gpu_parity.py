@@ -446,6 +446,11 @@ def test_error_behaviour(gpu):
         gpu.mc_eur(*P1, 100, "call", replay=np.zeros(50))      # replay stream too short
     with pytest.raises(ValueError):
         gpu.mc_eur(*P1, 0, "call")
+    # a path store that cannot fit (2e9 paths x 50 dates = 800 GB) is refused cleanly and the library stays usable
+    with pytest.raises(Exception) as ei:
+        gpu.mc_amer(*P1, 2_000_000_000, 50, "put")
+    assert getattr(ei.value, "status", None) == gpu.PCF_ENOMEM
+    assert gpu.mc_amer(*P1, 10_000, 10, "put", seed=1).price > 0
     # all paths identical (sigma = 0) with S > E: x'x is singular -> the reference throws (common.h:115-117)
     with pytest.raises(ValueError, match="Detereminant"):
         gpu.mc_amer(100, 90, .05, 0.0, 1, 1000, 10, "call")
