@@ -68,6 +68,10 @@ WORKLOADS = {
                                         "(every term pair through the full-accuracy saddle-point routine)",
                                  N=100_000_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
                                  kernel="binom_terms_kernel"),
+    "binom_embar_max": dict(config="binom_embar call 100/100/.05/.2/1, N=2147483647 steps (the reference's int limit; SURVEY 8d "
+                                   "quotes the binomial roofline at this size)",
+                            N=2_147_483_647, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
+                            kernel="binom_terms_kernel"),
     # SURVEY 8(f).1 (widening row): algorithmic work = the recurrence as the reference writes it with tabulated powers:
     # 2 mul + add + IEEE division (10 slots, libdevice) [+ 2 mul, payoff 2, max 1 for the American tree]
     "binom_vanilla_amer": dict(config="binom_vanilla_amer put 100/100/.05/.2/1, N=1e5 layers (SURVEY 8f.1; the reference "
@@ -99,6 +103,8 @@ def run_ours_once(pcf, name, seed, N=None):
     if name == "mc_amer":
         return pcf.mc_amer(*a, N, w["M"], "put", seed=seed)
     if name == "binom_embar":
+        return pcf.binom(*a, N, "call")
+    if name == "binom_embar_max":
         return pcf.binom(*a, N, "call")
     if name == "binom_embar_noscreen":
         return pcf.binom(*a, N, "call", screen=False)
@@ -201,7 +207,7 @@ def cpu_reference_other(name, threads):
             sec = float(oracle.ref_row("mc_amer_omp", "put", *a, n, M, threads)[12])
             return {"value": n * M / sec, "unit": "path-steps/s", "cores": threads, "kind": "reference",
                     "sample": f"{n} of 1e8 paths x {M} dates, {sec:.1f} s, mc_amer_omp (unmodified reference source, -O2)"}
-        if name in ("binom_embar", "binom_embar_noscreen"):
+        if name in ("binom_embar", "binom_embar_noscreen", "binom_embar_max"):
             n = 50_000
             sec = float(oracle.ref_row("binom_embar_omp", "call", *a, n, threads)[12])
             return {"value": (n + 1) / sec, "unit": "terms/s", "cores": threads, "kind": "reference",
@@ -390,6 +396,8 @@ def main():
                                # a path that does not shard (the tree) runs as replicas: its rate is per GPU already
                                "roofline": roofline_for(other, ups if WORKLOADS[other].get("replicas") else ups / n_gpus,
                                                         fp64_peak, hbm, hbm_src)})
+                if "assets" in WORKLOADS[other]:  # the basket is also quoted in asset-steps
+                    others[-1]["asset_steps_per_sec"] = ups * WORKLOADS[other]["assets"]
                 if job.rank == 0 and n_gpus == 1 and not args.no_cpu:
                     others[-1]["cpu_baseline"] = cpu_reference_other(other, host_threads())
             except Exception as ex:  # e.g. the path store does not fit
@@ -402,6 +410,16 @@ def main():
         cpu = {"value": v, "unit": "path-steps/s", "cores": threads, "kind": kind,
                "sample": f"{args.cpu_paths} of 1e9 paths x 252 dates, {sec:.1f} s, mc_asia_omp "
                          + ("(unmodified reference source, -O2)" if kind == "reference" else "(oracle port)")}
+        try:  # the reference ships without -O (Makefile:9); reported next to the -O2 headline
+            import oracle
+            if kind == "reference" and os.path.exists(os.path.join(oracle.REF_DIR, "mc_asia_omp_O0")):
+                n0 = max(args.cpu_paths // 4, 1000)
+                row = oracle.ref_row("mc_asia_omp_O0", "call", 100, 100, 0.05, 0.2, 1, n0, 252, threads)
+                cpu["as_shipped_no_O"] = {"value": n0 * 252 / float(row[12]), "unit": "path-steps/s",
+                                          "sample": f"{n0} paths x 252 dates, {float(row[12]):.1f} s, mc_asia_omp built with "
+                                                    "the reference's own flags (no -O, Makefile:9)"}
+        except Exception as ex:
+            cpu["as_shipped_no_O"] = {"error": str(ex)}
 
     if job.rank == 0:
         line = {
