@@ -78,7 +78,7 @@ WORKLOADS = {
                                       "needs ~45 s per tree at this size)",
                                N=100_000, M=0, steps_per_unit=1, slots=18.0, bound="fp64", unit="node-updates/s",
                                algo_src="DESIGN 4.5: 2 mul + add + IEEE division 10 + 2 mul + payoff 2 + max 1",
-                               kernel="tree_steps_kernel", replicas=True),
+                               kernel="tree_cta_kernel", replicas=True),
 }
 
 

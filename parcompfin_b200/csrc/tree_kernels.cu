@@ -40,6 +40,7 @@ struct TreeArgs {
   long long n0;
   int steps;           // <= kSteps
   int trig;            // programmatic dependent launch: 1 = release the next launch at kernel start, 2 = after the layers
+  int stride;          // tree_cta_kernel: nodes a CTA finishes per launch
   double p, q, R, z;   // z = RN(1/R)
   double S0, sgn, nE;  // payoff(S) = max(fma(sgn, S, nE), 0) = max(cp*(S - E), 0)
 };
@@ -140,6 +141,114 @@ __global__ void __launch_bounds__(kTreeWarps * 32) tree_steps_kernel(TreeArgs a)
   }
 }
 
+// CTA-cooperative trapezoid (see the header). Geometry, all in CTA-local node positions c = warp*kOwn + lane*kR + j:
+//   kL = 32 kR nodes per warp, kOwn = kL - kH of them owned, kC = kW kOwn + kH nodes per CTA; after s layers the
+//   positions [0, kC - s) are exact, so a launch of a.steps <= kK layers finishes a.stride = kC - kK of them.
+template <int kR, int kW>
+struct CtaShape {
+  static constexpr int kH = kR == 3 ? 9 : kR == 6 ? 12 : 8;  // halo layers: a whole number of lanes
+  static constexpr int kL = 32 * kR;
+  static constexpr int kOwn = kL - kH;
+  static constexpr int kC = kW * kOwn + kH;
+  static constexpr int kK = kC >= 440 ? 128 : 64;            // layers per launch
+  static constexpr int kStride = kC - kK;
+};
+
+template <int kR, int kW, bool kAmer>
+__global__ void __launch_bounds__(kW * 32) tree_cta_kernel(TreeArgs a) {
+  using Sh = CtaShape<kR, kW>;
+  constexpr int kH = Sh::kH, kOwn = Sh::kOwn, kC = Sh::kC, kK = Sh::kK;
+  static_assert(kH % kR == 0 && kH >= kR && kH < 32 * kR, "halo must be a whole number of lanes");
+  static_assert(kC > kK && kK >= kH, "a launch must finish at least one node per CTA");
+  constexpr int kHaloLanes = kH / kR;
+  constexpr int kWin = kK + kC - 1;           // d-power window of the CTA (unpadded entries)
+  constexpr int kPad = kWin + kWin / 16 + 2;  // index k + (k >> 4): conflict-free LDS.64 at lane stride kR
+  __shared__ double s_pd[kAmer ? kPad : 1];
+  __shared__ double s_x[2][kW][kH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long base = (long long)blockIdx.x * a.stride;
+  const long long n_out = a.n0 - a.steps;
+  if (base > n_out) return;  // whole CTA: no barrier is skipped by part of a block
+  const int c0 = warp * kOwn + lane * kR;
+  const long long i0 = base + c0;
+  if (a.trig == 1) asm volatile("griddepcontrol.launch_dependents;");
+
+  double v[kR], A[kR], W[kR];
+  // window entry k holds pd[lo + k]; node c of the layer reached after s+1 layers (n = n0 - 1 - s) needs
+  // pd[n - base - c] = entry (steps - 1 - s) + (kC - 1 - c)
+  const long long lo = a.n0 - a.steps - base - kC + 1;
+  if (kAmer) {
+#pragma unroll
+    for (int j = 0; j < kR; ++j) {
+      const long long i = i0 + j;
+      A[j] = (i <= a.n0) ? __dmul_rn(a.S0, a.pu[i]) : 0.0;  // S0*pow(u,i), binom_vanilla_amer.cpp:33
+    }
+    const int win = a.steps + kC - 1;
+    for (int k = threadIdx.x; k < win; k += kW * 32) {
+      const long long idx = lo + k;
+      s_pd[k + (k >> 4)] = (idx >= 0 && idx <= a.n0) ? a.pd[idx] : 0.0;
+    }
+    __syncthreads();
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < kR; ++j) {
+    const long long i = i0 + j;
+    v[j] = (i <= a.n0) ? a.vin[i] : 0.0;
+  }
+  // the lane keeps entries t = s .. s+kR-1 (t = s + j) in W[t % kR]; entry t is window index kbase - t
+  const int kbase = a.steps - 1 + kC - 1 - c0;
+  if (kAmer) {
+#pragma unroll
+    for (int t = 0; t < kR; ++t) {
+      const int k = kbase - t;
+      W[t] = (k >= 0) ? s_pd[k + (k >> 4)] : 0.0;
+    }
+  }
+  const int rounds = (a.steps + kH - 1) / kH;
+  for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+    for (int ss = 0; ss < kH; ++ss) {  // kH % kR == 0, so (r kH + ss) % kR == ss % kR: register indices are static
+      const int s = r * kH + ss;
+      if (s < a.steps) {  // block-uniform
+        const double halo = __shfl_down_sync(0xffffffffu, v[0], 1);  // lane 31: the warp's halo decays by one node
+#pragma unroll
+        for (int j = 0; j < kR; ++j) {
+          const double hi = (j + 1 < kR) ? v[j + 1] : halo;
+          double nv = tree_node(v[j], hi, a);
+          if (kAmer) {
+            const double c = fma(a.sgn, __dmul_rn(A[j], W[(ss + j) % kR]), a.nE);  // binom_vanilla_amer.cpp:33-35
+            const double sij = c > 0.0 ? c : 0.0;
+            nv = (nv < sij) ? sij : nv;
+          }
+          v[j] = nv;
+        }
+        if (kAmer) {
+          const int k = kbase - (s + kR);  // entry t = s + kR replaces t = s
+          W[ss % kR] = (k >= 0) ? s_pd[k + (k >> 4)] : 0.0;
+        }
+      }
+    }
+    if (r + 1 < rounds) {  // refill every warp's halo from its right neighbour's first kH nodes
+      if (lane < kHaloLanes) {
+#pragma unroll
+        for (int j = 0; j < kR; ++j) s_x[r & 1][warp][lane * kR + j] = v[j];
+      }
+      __syncthreads();  // one barrier per round: the buffers alternate
+      if (warp + 1 < kW && lane >= 32 - kHaloLanes) {
+#pragma unroll
+        for (int j = 0; j < kR; ++j) v[j] = s_x[r & 1][warp + 1][(lane - (32 - kHaloLanes)) * kR + j];
+      }
+    }
+  }
+  if (a.trig == 2) asm volatile("griddepcontrol.launch_dependents;");
+#pragma unroll
+  for (int j = 0; j < kR; ++j) {
+    const long long i = i0 + j;
+    if (lane * kR + j < kOwn && c0 + j < a.stride && i <= n_out) a.vout[i] = v[j];
+  }
+}
+
 // terminal layer: eur max((S-E)*cp, 0) (binom_vanilla_eur.cpp:30), amer payoff(S,E,cp) (binom_vanilla_amer.cpp:29) --
 // the same value (multiplication by +-1 is exact)
 __global__ void tree_terminal_kernel(double* __restrict__ v, const double* __restrict__ pu, const double* __restrict__ pd,
@@ -194,6 +303,77 @@ static int tree_launch_all(Ctx& c, TreeArgs a, long long N, bool amer, double* b
   return PCF_OK;
 }
 
+// ---- per-launch shape selection for tree_cta_kernel -------------------------------------------------------------
+struct CtaCandidate {
+  int kR, kW, kK, stride;
+  void (*eur)(TreeArgs);
+  void (*amer)(TreeArgs);
+};
+#define PCF_CTA_SHAPE(R, W) \
+  { R, W, CtaShape<R, W>::kK, CtaShape<R, W>::kStride, tree_cta_kernel<R, W, false>, tree_cta_kernel<R, W, true> }
+static const CtaCandidate kCtaShapes[] = {
+    PCF_CTA_SHAPE(1, 8),  PCF_CTA_SHAPE(1, 16), PCF_CTA_SHAPE(1, 20), PCF_CTA_SHAPE(2, 8),  PCF_CTA_SHAPE(2, 12),
+    PCF_CTA_SHAPE(2, 16), PCF_CTA_SHAPE(3, 8),  PCF_CTA_SHAPE(3, 12), PCF_CTA_SHAPE(3, 16), PCF_CTA_SHAPE(4, 12),
+    PCF_CTA_SHAPE(4, 16), PCF_CTA_SHAPE(6, 12), PCF_CTA_SHAPE(6, 16), PCF_CTA_SHAPE(8, 16), PCF_CTA_SHAPE(8, 20),
+};
+#undef PCF_CTA_SHAPE
+
+// Cost of one layer of an n0-node layer in units of "one FP64 node chain per lane and SM sub-partition": the busiest
+// SM holds ceil(grid / SMs) CTAs, i.e. that many times kW/4 warps of kR nodes per lane on each of its four
+// sub-partitions; below ~4 the dependent chain of one layer (five FP64 operations + a shuffle), not the pipe, sets the
+// pace; the prologue/epilogue of a launch costs about as much as 8 such units of one layer (ncu, profiles/r1p_*).
+static const CtaCandidate& tree_pick_shape(long long n0, int sms, int fixed_r, int fixed_w) {
+  const CtaCandidate* best = nullptr;
+  double best_cost = 0.0;
+  for (const CtaCandidate& s : kCtaShapes) {
+    if (fixed_r && (s.kR != fixed_r || s.kW != fixed_w)) continue;
+    const long long steps = std::min<long long>(s.kK, n0);
+    const long long grid = (n0 - steps + 1 + s.stride - 1) / s.stride;
+    const long long per_sm = (grid + sms - 1) / sms;
+    const double chain = (double)per_sm * ((s.kW + 3) / 4) * s.kR;
+    const double cost = std::max(chain, 4.0) + 8.0 * 16.0 / (double)s.kK;
+    if (!best || cost < best_cost) { best = &s; best_cost = cost; }
+  }
+  return best ? *best : kCtaShapes[0];
+}
+
+// fixed_r/fixed_w != 0 pin one shape for the whole tree (PCF_TREE=1<R><WW>, tests and tuning)
+static int tree_launch_cta(Ctx& c, TreeArgs a, long long N, bool amer, double* buf0, double* buf1, int fixed_r, int fixed_w) {
+  const char* pe = getenv("PCF_TREE_PDL");
+  const int trig = pe ? atoi(pe) : 2;
+  a.trig = trig;
+  long long n = N;
+  double* in = buf0;
+  double* out = buf1;
+  while (n > 0) {
+    const CtaCandidate& s = tree_pick_shape(n, c.sm_count, fixed_r, fixed_w);
+    if (fixed_r && (s.kR != fixed_r || s.kW != fixed_w)) {
+      set_last_error("unknown PCF_TREE");
+      return PCF_EINVAL;
+    }
+    const int steps = (int)std::min<long long>(s.kK, n);
+    a.vin = in; a.vout = out; a.n0 = n; a.steps = steps; a.stride = s.stride;
+    const long long grid = (n - steps + 1 + s.stride - 1) / s.stride;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(s.kW * 32);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = trig != 0 ? 1 : 0;
+    PCF_CUDA(cudaLaunchKernelEx(&cfg, amer ? s.amer : s.eur, a));
+    c.launches++;
+    n -= steps;
+    std::swap(in, out);
+  }
+  PCF_CUDA(cudaMemcpyAsync(c.d_out, in, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  PCF_CUDA(cudaGetLastError());
+  return PCF_OK;
+}
+
 // pow tables with the reference's own libm call, spread over the host's cores (2(N+1) calls; a serial loop would
 // cost as much as the whole device computation at N = 1e5)
 static void pow_table(double base, long long N, double* out) {
@@ -238,9 +418,13 @@ int run_binom_tree(Ctx& c, const pcf_params& p, bool american) {
   a.S0 = p.S0; a.sgn = (double)p.cp; a.nE = -a.sgn * p.E;
   tree_terminal_kernel<<<grid_for(c, N + 1, 256, 8), 256, 0, c.stream>>>(buf0, d_pu, d_pd, N, p.S0, a.sgn, a.nE);
   c.launches++;
-  // launch shape: PCF_TREE = <nodes per lane><layers per launch / 8>  (tuning knob)
+  // launch shape (tuning knob): unset = CTA-cooperative kernel, shape chosen per launch; PCF_TREE=1<nodes per lane>
+  // <warps per CTA, two digits> pins one CTA shape (e.g. 1216); PCF_TREE=<nodes per lane><layers per launch / 8> selects the warp-trapezoid
+  // kernel of the first build
   const char* e = getenv("PCF_TREE");
-  const int shape = e ? atoi(e) : (N > 250000 ? 44 : 48);  // wide trees: less redundancy (1.33x) beats fewer launches
+  if (!e) return tree_launch_cta(c, a, N, american, buf0, buf1, 0, 0);
+  const int shape = atoi(e);
+  if (shape >= 1000 && shape < 2000) return tree_launch_cta(c, a, N, american, buf0, buf1, (shape / 100) % 10, shape % 100);
   switch (shape) {
     case 22: return tree_launch_all<2, 16>(c, a, N, american, buf0, buf1);
     case 44: return tree_launch_all<4, 32>(c, a, N, american, buf0, buf1);

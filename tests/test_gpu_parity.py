@@ -334,14 +334,19 @@ def test_trees_launch_shape_independence_and_properties(gpu, monkeypatch):
     # the tiling (nodes per lane x layers per launch) must not change a single bit: same operations per node
     P = (100, 100, .05, .2, 1)
     ref = {}
-    for shape in ("44", "22", "48", "88", "84"):
-        monkeypatch.setenv("PCF_TREE", shape)
-        for N in (1, 5, 31, 97, 1000, 5003):
+    # None: CTA-cooperative kernel, shape picked per launch (the default); 1<R><WW>: one pinned CTA shape (nodes per
+    # lane, warps per CTA); 2-digit shapes: the warp-trapezoid kernel
+    for shape in (None, "44", "22", "48", "88", "84", "1108", "1120", "1208", "1216", "1312", "1416", "1612", "1820"):
+        if shape is None:
+            monkeypatch.delenv("PCF_TREE", raising=False)
+        else:
+            monkeypatch.setenv("PCF_TREE", shape)
+        for N in (1, 5, 31, 97, 1000, 5003, 20011):
             for pf in ("call", "put"):
                 e = gpu.binom_vanilla_eur(*P, N, pf).price
                 a = gpu.binom_vanilla_amer(*P, N, pf).price
                 assert ref.setdefault((N, pf), (e, a)) == (e, a), (shape, N, pf)
-    monkeypatch.delenv("PCF_TREE")
+    monkeypatch.delenv("PCF_TREE", raising=False)
     # small trees against the oracle, including N not a multiple of anything
     for N in (1, 2, 3, 17, 200, 777):
         for pf in ("call", "put"):
