@@ -212,18 +212,30 @@ __global__ void __launch_bounds__(kW * 32) tree_cta_kernel(TreeArgs a) {
       const int s = r * kH + ss;
       if (s < a.steps) {  // block-uniform
         const double halo = __shfl_down_sync(0xffffffffu, v[0], 1);  // lane 31: the warp's halo decays by one node
+        // The kR nodes of a lane are independent within a layer. Written node by node, ptxas keeps each node's
+        // six-instruction dependent chain contiguous (one scratch register pair, kR x 48 cycles per layer); written
+        // stage by stage it issues the kR chains interleaved, which is what keeps the FP64 pipe busy.
+        double x[kR], q0[kR], sij[kR];
 #pragma unroll
-        for (int j = 0; j < kR; ++j) {
-          const double hi = (j + 1 < kR) ? v[j + 1] : halo;
-          double nv = tree_node(v[j], hi, a);
-          if (kAmer) {
-            const double c = fma(a.sgn, __dmul_rn(A[j], W[(ss + j) % kR]), a.nE);  // binom_vanilla_amer.cpp:33-35
-            const double sij = c > 0.0 ? c : 0.0;
-            nv = (nv < sij) ? sij : nv;
-          }
-          v[j] = nv;
-        }
+        for (int j = 0; j < kR; ++j) x[j] = __dmul_rn(a.q, v[j]);
+#pragma unroll
+        for (int j = 0; j < kR; ++j) x[j] = __dadd_rn(__dmul_rn(a.p, (j + 1 < kR) ? v[j + 1] : halo), x[j]);
+#pragma unroll
+        for (int j = 0; j < kR; ++j) q0[j] = __dmul_rn(x[j], a.z);
         if (kAmer) {
+#pragma unroll
+          for (int j = 0; j < kR; ++j) {
+            const double c = fma(a.sgn, __dmul_rn(A[j], W[(ss + j) % kR]), a.nE);  // binom_vanilla_amer.cpp:33-35
+            sij[j] = c > 0.0 ? c : 0.0;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kR; ++j) x[j] = fma(-q0[j], a.R, x[j]);
+#pragma unroll
+        for (int j = 0; j < kR; ++j) v[j] = fma(x[j], a.z, q0[j]);
+        if (kAmer) {
+#pragma unroll
+          for (int j = 0; j < kR; ++j) v[j] = (v[j] < sij[j]) ? sij[j] : v[j];
           const int k = kbase - (s + kR);  // entry t = s + kR replaces t = s
           W[ss % kR] = (k >= 0) ? s_pd[k + (k >> 4)] : 0.0;
         }
@@ -312,29 +324,39 @@ struct CtaCandidate {
 #define PCF_CTA_SHAPE(R, W) \
   { R, W, CtaShape<R, W>::kK, CtaShape<R, W>::kStride, tree_cta_kernel<R, W, false>, tree_cta_kernel<R, W, true> }
 static const CtaCandidate kCtaShapes[] = {
-    PCF_CTA_SHAPE(1, 8),  PCF_CTA_SHAPE(1, 16), PCF_CTA_SHAPE(1, 20), PCF_CTA_SHAPE(2, 8),  PCF_CTA_SHAPE(2, 12),
-    PCF_CTA_SHAPE(2, 16), PCF_CTA_SHAPE(3, 8),  PCF_CTA_SHAPE(3, 12), PCF_CTA_SHAPE(3, 16), PCF_CTA_SHAPE(4, 12),
-    PCF_CTA_SHAPE(4, 16), PCF_CTA_SHAPE(6, 12), PCF_CTA_SHAPE(6, 16), PCF_CTA_SHAPE(8, 16), PCF_CTA_SHAPE(8, 20),
+    PCF_CTA_SHAPE(2, 4),  PCF_CTA_SHAPE(3, 4),  PCF_CTA_SHAPE(4, 4),  PCF_CTA_SHAPE(6, 4),  PCF_CTA_SHAPE(8, 4),
+    PCF_CTA_SHAPE(1, 8),  PCF_CTA_SHAPE(2, 8),  PCF_CTA_SHAPE(3, 8),  PCF_CTA_SHAPE(4, 8),  PCF_CTA_SHAPE(6, 8),
+    PCF_CTA_SHAPE(8, 8),  PCF_CTA_SHAPE(2, 12), PCF_CTA_SHAPE(3, 12), PCF_CTA_SHAPE(4, 12), PCF_CTA_SHAPE(6, 12),
+    PCF_CTA_SHAPE(8, 12), PCF_CTA_SHAPE(1, 16), PCF_CTA_SHAPE(2, 16), PCF_CTA_SHAPE(3, 16), PCF_CTA_SHAPE(4, 16),
+    PCF_CTA_SHAPE(6, 16), PCF_CTA_SHAPE(8, 16), PCF_CTA_SHAPE(1, 20), PCF_CTA_SHAPE(8, 20),
 };
 #undef PCF_CTA_SHAPE
 
-// Cost of one layer of an n0-node layer in units of "one FP64 node chain per lane and SM sub-partition": the busiest
-// SM holds ceil(grid / SMs) CTAs, i.e. that many times kW/4 warps of kR nodes per lane on each of its four
-// sub-partitions; below ~4 the dependent chain of one layer (five FP64 operations + a shuffle), not the pipe, sets the
-// pace; the prologue/epilogue of a launch costs about as much as 8 such units of one layer (ncu, profiles/r1p_*).
-static const CtaCandidate& tree_pick_shape(long long n0, int sms, int fixed_r, int fixed_w) {
-  const CtaCandidate* best = nullptr;
-  double best_cost = 0.0;
-  for (const CtaCandidate& s : kCtaShapes) {
-    if (fixed_r && (s.kR != fixed_r || s.kW != fixed_w)) continue;
-    const long long steps = std::min<long long>(s.kK, n0);
-    const long long grid = (n0 - steps + 1 + s.stride - 1) / s.stride;
-    const long long per_sm = (grid + sms - 1) / sms;
-    const double chain = (double)per_sm * ((s.kW + 3) / 4) * s.kR;
-    const double cost = std::max(chain, 4.0) + 8.0 * 16.0 / (double)s.kK;
-    if (!best || cost < best_cost) { best = &s; best_cost = cost; }
-  }
-  return best ? *best : kCtaShapes[0];
+// Shape of the launch that starts at an n0-node layer. The table is MEASURED (tests/tune_tree4.py: T(N) of every pinned
+// shape on a grid of N; the slope between two grid points is the cost of one layer at that width; the cheapest shape
+// per interval is listed, profiles/r1p_tune_tree_shapes.log) on a 148-SM B200 and scaled by the SM count. What it
+// encodes: (1) ptxas interleaves the independent node chains of a lane for kR <= 4 but serialises them for kR >= 6
+// (one scratch register pair per node), so more than four nodes per lane only pay when the layer is many waves wide;
+// (2) the FP64 pipe interleaves the chains of ONE warp better than those of several warps (tests/ubench: 8 warps x 1
+// chain 3.0 cycles per instruction, 1 warp x 4 chains 2.2), so the European tree prefers one kR = 4 warp per
+// sub-partition; (3) the American node needs twice the registers and its kR = 4 schedule is poorer, so it prefers
+// kR = 2 with more warps until the layer is wider than one wave.
+struct ShapeRule { long long n_max; int kR, kW; };
+static const ShapeRule kRulesEur[] = {{50000, 4, 4}, {80000, 3, 8}, {300000, 4, 4}, {-1, 4, 8}};
+static const ShapeRule kRulesAmer[] = {{20000, 2, 4}, {50000, 2, 8}, {80000, 2, 12}, {100000, 2, 8}, {150000, 3, 12},
+                                       {300000, 6, 4}, {500000, 4, 12}, {-1, 6, 8}};
+
+static const CtaCandidate* tree_find_shape(int kR, int kW) {
+  for (const CtaCandidate& s : kCtaShapes)
+    if (s.kR == kR && s.kW == kW) return &s;
+  return nullptr;
+}
+
+static const CtaCandidate* tree_pick_shape(long long n0, int sms, bool amer, int fixed_r, int fixed_w) {
+  if (fixed_r) return tree_find_shape(fixed_r, fixed_w);
+  const double scaled = (double)n0 * 148.0 / (double)std::max(sms, 1);
+  for (const ShapeRule* r = amer ? kRulesAmer : kRulesEur;; ++r)
+    if (r->n_max < 0 || scaled <= (double)r->n_max) return tree_find_shape(r->kR, r->kW);
 }
 
 // fixed_r/fixed_w != 0 pin one shape for the whole tree (PCF_TREE=1<R><WW>, tests and tuning)
@@ -346,11 +368,12 @@ static int tree_launch_cta(Ctx& c, TreeArgs a, long long N, bool amer, double* b
   double* in = buf0;
   double* out = buf1;
   while (n > 0) {
-    const CtaCandidate& s = tree_pick_shape(n, c.sm_count, fixed_r, fixed_w);
-    if (fixed_r && (s.kR != fixed_r || s.kW != fixed_w)) {
+    const CtaCandidate* ps = tree_pick_shape(n, c.sm_count, amer, fixed_r, fixed_w);
+    if (!ps) {
       set_last_error("unknown PCF_TREE");
       return PCF_EINVAL;
     }
+    const CtaCandidate& s = *ps;
     const int steps = (int)std::min<long long>(s.kK, n);
     a.vin = in; a.vout = out; a.n0 = n; a.steps = steps; a.stride = s.stride;
     const long long grid = (n - steps + 1 + s.stride - 1) / s.stride;

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import parcompfin_b200 as pcf
 pcf.init(1)
 P = (100., 100., .05, .2, 1.)
-shapes = sys.argv[1:] or ["auto", "48", "44", "1208", "1216", "1312", "1416", "1616", "1820"]
+shapes = sys.argv[1:] or ["auto", "44", "1208", "1312", "1404", "1604", "1804", "1408", "1608", "1808", "1812"]
 ref = {}
 for N in (10_000, 100_000, 400_000, 1_000_000):
     for shape in shapes:
