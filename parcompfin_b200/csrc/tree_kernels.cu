@@ -144,19 +144,19 @@ __global__ void __launch_bounds__(kTreeWarps * 32) tree_steps_kernel(TreeArgs a)
 // CTA-cooperative trapezoid (see the header). Geometry, all in CTA-local node positions c = warp*kOwn + lane*kR + j:
 //   kL = 32 kR nodes per warp, kOwn = kL - kH of them owned, kC = kW kOwn + kH nodes per CTA; after s layers the
 //   positions [0, kC - s) are exact, so a launch of a.steps <= kK layers finishes a.stride = kC - kK of them.
-template <int kR, int kW>
+template <int kR, int kW, int kKsel>
 struct CtaShape {
   static constexpr int kH = kR == 3 ? 9 : kR == 6 ? 12 : 8;  // halo layers: a whole number of lanes
   static constexpr int kL = 32 * kR;
   static constexpr int kOwn = kL - kH;
   static constexpr int kC = kW * kOwn + kH;
-  static constexpr int kK = kC >= 440 ? 128 : 64;            // layers per launch
+  static constexpr int kK = kKsel ? kKsel : (kC >= 440 ? 128 : 64);  // layers per launch (0 = default)
   static constexpr int kStride = kC - kK;
 };
 
-template <int kR, int kW, bool kAmer>
+template <int kR, int kW, int kKsel, bool kAmer>
 __global__ void __launch_bounds__(kW * 32) tree_cta_kernel(TreeArgs a) {
-  using Sh = CtaShape<kR, kW>;
+  using Sh = CtaShape<kR, kW, kKsel>;
   constexpr int kH = Sh::kH, kOwn = Sh::kOwn, kC = Sh::kC, kK = Sh::kK;
   static_assert(kH % kR == 0 && kH >= kR && kH < 32 * kR, "halo must be a whole number of lanes");
   static_assert(kC > kK && kK >= kH, "a launch must finish at least one node per CTA");
@@ -317,20 +317,25 @@ static int tree_launch_all(Ctx& c, TreeArgs a, long long N, bool amer, double* b
 
 // ---- per-launch shape selection for tree_cta_kernel -------------------------------------------------------------
 struct CtaCandidate {
-  int kR, kW, kK, stride;
+  int kR, kW, kKsel, kK, stride;
   void (*eur)(TreeArgs);
   void (*amer)(TreeArgs);
 };
-#define PCF_CTA_SHAPE(R, W) \
-  { R, W, CtaShape<R, W>::kK, CtaShape<R, W>::kStride, tree_cta_kernel<R, W, false>, tree_cta_kernel<R, W, true> }
+#define PCF_CTA_SHAPE_K(R, W, K) \
+  { R, W, K, CtaShape<R, W, K>::kK, CtaShape<R, W, K>::kStride, tree_cta_kernel<R, W, K, false>, tree_cta_kernel<R, W, K, true> }
+#define PCF_CTA_SHAPE(R, W) PCF_CTA_SHAPE_K(R, W, 0)
 static const CtaCandidate kCtaShapes[] = {
     PCF_CTA_SHAPE(2, 4),  PCF_CTA_SHAPE(3, 4),  PCF_CTA_SHAPE(4, 4),  PCF_CTA_SHAPE(6, 4),  PCF_CTA_SHAPE(8, 4),
     PCF_CTA_SHAPE(1, 8),  PCF_CTA_SHAPE(2, 8),  PCF_CTA_SHAPE(3, 8),  PCF_CTA_SHAPE(4, 8),  PCF_CTA_SHAPE(6, 8),
     PCF_CTA_SHAPE(8, 8),  PCF_CTA_SHAPE(2, 12), PCF_CTA_SHAPE(3, 12), PCF_CTA_SHAPE(4, 12), PCF_CTA_SHAPE(6, 12),
     PCF_CTA_SHAPE(8, 12), PCF_CTA_SHAPE(1, 16), PCF_CTA_SHAPE(2, 16), PCF_CTA_SHAPE(3, 16), PCF_CTA_SHAPE(4, 16),
     PCF_CTA_SHAPE(6, 16), PCF_CTA_SHAPE(8, 16), PCF_CTA_SHAPE(1, 20), PCF_CTA_SHAPE(8, 20),
+    // 256 layers per launch: half the launches where the layer is narrow enough to afford the wider decaying edge
+    // (measured: 105 instead of 115 cycles per layer below 30 k nodes; wider shapes gain nothing from it)
+    PCF_CTA_SHAPE_K(4, 4, 256), PCF_CTA_SHAPE_K(3, 8, 256), PCF_CTA_SHAPE_K(2, 8, 256), PCF_CTA_SHAPE_K(2, 12, 256),
 };
 #undef PCF_CTA_SHAPE
+#undef PCF_CTA_SHAPE_K
 
 // Shape of the launch that starts at an n0-node layer. The table is MEASURED (tests/tune_tree4.py: T(N) of every pinned
 // shape on a grid of N; the slope between two grid points is the cost of one layer at that width; the cheapest shape
@@ -341,26 +346,29 @@ static const CtaCandidate kCtaShapes[] = {
 // chain 3.0 cycles per instruction, 1 warp x 4 chains 2.2), so the European tree prefers one kR = 4 warp per
 // sub-partition; (3) the American node needs twice the registers and its kR = 4 schedule is poorer, so it prefers
 // kR = 2 with more warps until the layer is wider than one wave.
-struct ShapeRule { long long n_max; int kR, kW; };
-static const ShapeRule kRulesEur[] = {{50000, 4, 4}, {80000, 3, 8}, {300000, 4, 4}, {-1, 4, 8}};
-static const ShapeRule kRulesAmer[] = {{20000, 2, 4}, {50000, 2, 8}, {80000, 2, 12}, {100000, 2, 8}, {150000, 3, 12},
-                                       {300000, 6, 4}, {500000, 4, 12}, {-1, 6, 8}};
+struct ShapeRule { long long n_max; int kR, kW, kKsel; };
+static const ShapeRule kRulesEur[] = {{30000, 4, 4, 256}, {50000, 4, 4, 0}, {60000, 3, 8, 256}, {80000, 3, 8, 0},
+                                      {300000, 4, 4, 0}, {-1, 4, 8, 0}};
+static const ShapeRule kRulesAmer[] = {{30000, 2, 8, 256}, {50000, 2, 8, 0}, {60000, 2, 12, 256}, {80000, 2, 12, 0},
+                                       {100000, 2, 8, 0}, {150000, 3, 12, 0}, {300000, 6, 4, 0}, {500000, 4, 12, 0},
+                                       {-1, 6, 8, 0}};
 
-static const CtaCandidate* tree_find_shape(int kR, int kW) {
+static const CtaCandidate* tree_find_shape(int kR, int kW, int kKsel) {
   for (const CtaCandidate& s : kCtaShapes)
-    if (s.kR == kR && s.kW == kW) return &s;
+    if (s.kR == kR && s.kW == kW && s.kKsel == kKsel) return &s;
   return nullptr;
 }
 
-static const CtaCandidate* tree_pick_shape(long long n0, int sms, bool amer, int fixed_r, int fixed_w) {
-  if (fixed_r) return tree_find_shape(fixed_r, fixed_w);
+static const CtaCandidate* tree_pick_shape(long long n0, int sms, bool amer, int fixed_r, int fixed_w, int fixed_k) {
+  if (fixed_r) return tree_find_shape(fixed_r, fixed_w, fixed_k);
   const double scaled = (double)n0 * 148.0 / (double)std::max(sms, 1);
   for (const ShapeRule* r = amer ? kRulesAmer : kRulesEur;; ++r)
-    if (r->n_max < 0 || scaled <= (double)r->n_max) return tree_find_shape(r->kR, r->kW);
+    if (r->n_max < 0 || scaled <= (double)r->n_max) return tree_find_shape(r->kR, r->kW, r->kKsel);
 }
 
-// fixed_r/fixed_w != 0 pin one shape for the whole tree (PCF_TREE=1<R><WW>, tests and tuning)
-static int tree_launch_cta(Ctx& c, TreeArgs a, long long N, bool amer, double* buf0, double* buf1, int fixed_r, int fixed_w) {
+// fixed_r/fixed_w != 0 pin one shape for the whole tree (PCF_TREE=1<R><WW>[<K/64>], tests and tuning)
+static int tree_launch_cta(Ctx& c, TreeArgs a, long long N, bool amer, double* buf0, double* buf1, int fixed_r, int fixed_w,
+                           int fixed_k) {
   const char* pe = getenv("PCF_TREE_PDL");
   const int trig = pe ? atoi(pe) : 2;
   a.trig = trig;
@@ -368,7 +376,7 @@ static int tree_launch_cta(Ctx& c, TreeArgs a, long long N, bool amer, double* b
   double* in = buf0;
   double* out = buf1;
   while (n > 0) {
-    const CtaCandidate* ps = tree_pick_shape(n, c.sm_count, amer, fixed_r, fixed_w);
+    const CtaCandidate* ps = tree_pick_shape(n, c.sm_count, amer, fixed_r, fixed_w, fixed_k);
     if (!ps) {
       set_last_error("unknown PCF_TREE");
       return PCF_EINVAL;
@@ -442,12 +450,14 @@ int run_binom_tree(Ctx& c, const pcf_params& p, bool american) {
   tree_terminal_kernel<<<grid_for(c, N + 1, 256, 8), 256, 0, c.stream>>>(buf0, d_pu, d_pd, N, p.S0, a.sgn, a.nE);
   c.launches++;
   // launch shape (tuning knob): unset = CTA-cooperative kernel, shape chosen per launch; PCF_TREE=1<nodes per lane>
-  // <warps per CTA, two digits> pins one CTA shape (e.g. 1216); PCF_TREE=<nodes per lane><layers per launch / 8> selects the warp-trapezoid
+  // <warps per CTA, two digits>[<layers per launch / 64>] pins one CTA shape (e.g. 1216, 14044); PCF_TREE=<nodes per lane><layers per launch / 8> selects the warp-trapezoid
   // kernel of the first build
   const char* e = getenv("PCF_TREE");
-  if (!e) return tree_launch_cta(c, a, N, american, buf0, buf1, 0, 0);
+  if (!e) return tree_launch_cta(c, a, N, american, buf0, buf1, 0, 0, 0);
   const int shape = atoi(e);
-  if (shape >= 1000 && shape < 2000) return tree_launch_cta(c, a, N, american, buf0, buf1, (shape / 100) % 10, shape % 100);
+  if (shape >= 1000 && shape < 2000) return tree_launch_cta(c, a, N, american, buf0, buf1, (shape / 100) % 10, shape % 100, 0);
+  if (shape >= 10000 && shape < 20000)
+    return tree_launch_cta(c, a, N, american, buf0, buf1, (shape / 1000) % 10, (shape / 10) % 100, 64 * (shape % 10));
   switch (shape) {
     case 22: return tree_launch_all<2, 16>(c, a, N, american, buf0, buf1);
     case 44: return tree_launch_all<4, 32>(c, a, N, american, buf0, buf1);

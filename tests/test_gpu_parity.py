@@ -337,7 +337,7 @@ def test_trees_launch_shape_independence_and_properties(gpu, monkeypatch):
     # None: CTA-cooperative kernel, shape picked per launch (the default); 1<R><WW>: one pinned CTA shape (nodes per
     # lane, warps per CTA); 2-digit shapes: the warp-trapezoid kernel
     for shape in (None, "44", "22", "48", "88", "84", "1108", "1120", "1204", "1208", "1216", "1304", "1312",
-                  "1404", "1416", "1604", "1612", "1804", "1812", "1820"):
+                  "1404", "1416", "1604", "1612", "1804", "1812", "1820", "14044", "12084", "13084", "12124"):
         if shape is None:
             monkeypatch.delenv("PCF_TREE", raising=False)
         else:
