@@ -31,6 +31,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout whenever NCCL_DEBUG is
+# set on the box) goes to stderr instead. Set before anything loads libnccl.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 P = dict(S0=100.0, E=100.0, r=0.05, sigma=0.2, T=1.0)
 SEED0 = 20240229
@@ -241,7 +244,7 @@ def bench_reference(args, rank):
     sample = (f"{n_paths} of 1e9 paths x {w['M']} dates per step (oracle/_ref/mc_asia_omp -O2, unmodified reference "
               f"source, {threads} OpenMP threads)" if kind == "reference" else
               f"{n_paths} of 1e9 paths x {w['M']} dates per step (oracle/cpu_ref.cpp OpenMP twin, {threads} threads)")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "path_steps_per_sec", "value": value, "unit": "path-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(secs) / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -249,7 +252,7 @@ def bench_reference(args, rank):
         "config": {"workload": w["config"], "sample_paths_per_step": n_paths},
         "cpu_baseline": {"value": value, "unit": "path-steps/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def measure(pcf, dist, job, name, steps, warmup, N=None):
@@ -327,6 +330,29 @@ def _roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src):
             "peak_source": hbm_src}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line. Libraries loaded later (NCCL's version banner, torch.distributed) write to
+    file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the rest of the process and the JSON line
+    goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,6 +366,7 @@ def main():
     ap.add_argument("--no-others", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3:
         args.warmup = 3
 
@@ -441,7 +468,7 @@ def main():
             "clocks": clocks,
             "others": others,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.barrier(job)
     pcf.shutdown()
     dist.teardown(job)
