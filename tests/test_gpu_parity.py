@@ -353,6 +353,12 @@ def test_trees_launch_shape_independence_and_properties(gpu, monkeypatch):
         for pf in ("call", "put"):
             assert gpu.binom_vanilla_eur(*P, N, pf).price == oracle.binom_tree(*P, N, pf, False)
             assert gpu.binom_vanilla_amer(*P, N, pf).price == oracle.binom_tree(*P, N, pf, True)
+    # wide trees walk every rule of the per-launch shape table (csrc/tree_kernels.cu: tree_pick_shape)
+    N = 600_000
+    auto = (gpu.binom_vanilla_eur(*P, N, "put").price, gpu.binom_vanilla_amer(*P, N, "put").price)
+    monkeypatch.setenv("PCF_TREE", "44")
+    assert auto == (gpu.binom_vanilla_eur(*P, N, "put").price, gpu.binom_vanilla_amer(*P, N, "put").price)
+    monkeypatch.delenv("PCF_TREE")
     # full size (the reference needs 45 s per tree here): the European tree and the binomial formula price the same
     # lattice; early exercise is worth something for the put and nothing for the call (r > 0, no dividends)
     N = 100_000
