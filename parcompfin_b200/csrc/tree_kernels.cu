@@ -161,9 +161,8 @@ __global__ void __launch_bounds__(kW * 32) tree_cta_kernel(TreeArgs a) {
   static_assert(kH % kR == 0 && kH >= kR && kH < 32 * kR, "halo must be a whole number of lanes");
   static_assert(kC > kK && kK >= kH, "a launch must finish at least one node per CTA");
   constexpr int kHaloLanes = kH / kR;
-  constexpr int kWin = kK + kC - 1;           // d-power window of the CTA (unpadded entries)
-  constexpr int kPad = kWin + kWin / 16 + 2;  // index k + (k >> 4): conflict-free LDS.64 at lane stride kR
-  __shared__ double s_pd[kAmer ? kPad : 1];
+  constexpr int kWin = kK + kC - 1;  // d-power window of the CTA; entry k at s_pd[k + 1], s_pd[0] = 0 stands for k = -1
+  __shared__ double s_pd[kAmer ? kWin + 1 : 1];
   __shared__ double s_x[2][kW][kH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long base = (long long)blockIdx.x * a.stride;
@@ -186,8 +185,9 @@ __global__ void __launch_bounds__(kW * 32) tree_cta_kernel(TreeArgs a) {
     const int win = a.steps + kC - 1;
     for (int k = threadIdx.x; k < win; k += kW * 32) {
       const long long idx = lo + k;
-      s_pd[k + (k >> 4)] = (idx >= 0 && idx <= a.n0) ? a.pd[idx] : 0.0;
+      s_pd[k + 1] = (idx >= 0 && idx <= a.n0) ? a.pd[idx] : 0.0;
     }
+    if (threadIdx.x == 0) s_pd[0] = 0.0;
     __syncthreads();
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -196,14 +196,15 @@ __global__ void __launch_bounds__(kW * 32) tree_cta_kernel(TreeArgs a) {
     const long long i = i0 + j;
     v[j] = (i <= a.n0) ? a.vin[i] : 0.0;
   }
-  // the lane keeps entries t = s .. s+kR-1 (t = s + j) in W[t % kR]; entry t is window index kbase - t
+  // the lane keeps entries t = s .. s+kR-1 (t = s + j) in W[t % kR]; entry t is window index kbase - t >= -1
+  // (kC - 1 - c0 >= kR - 1 for every lane, t <= steps - 1 + kR), i.e. wp[-t]: one LDS with an immediate offset per layer
   const int kbase = a.steps - 1 + kC - 1 - c0;
+  const double* wp = s_pd + 1 + kbase;
+  double sgn = a.sgn, nE = a.nE;
   if (kAmer) {
+    asm volatile("" : "+d"(sgn), "+d"(nE));  // keep them in registers: ptxas otherwise reloads them (LDC) per layer
 #pragma unroll
-    for (int t = 0; t < kR; ++t) {
-      const int k = kbase - t;
-      W[t] = (k >= 0) ? s_pd[k + (k >> 4)] : 0.0;
-    }
+    for (int t = 0; t < kR; ++t) W[t] = wp[-t];
   }
   const int rounds = (a.steps + kH - 1) / kH;
   for (int r = 0; r < rounds; ++r) {
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(kW * 32) tree_cta_kernel(TreeArgs a) {
         // The kR nodes of a lane are independent within a layer. Written node by node, ptxas keeps each node's
         // six-instruction dependent chain contiguous (one scratch register pair, kR x 48 cycles per layer); written
         // stage by stage it issues the kR chains interleaved, which is what keeps the FP64 pipe busy.
-        double x[kR], q0[kR], sij[kR];
+        double x[kR], q0[kR], ex[kR];
 #pragma unroll
         for (int j = 0; j < kR; ++j) x[j] = __dmul_rn(a.q, v[j]);
 #pragma unroll
@@ -223,11 +224,11 @@ __global__ void __launch_bounds__(kW * 32) tree_cta_kernel(TreeArgs a) {
 #pragma unroll
         for (int j = 0; j < kR; ++j) q0[j] = __dmul_rn(x[j], a.z);
         if (kAmer) {
+          // cp*(S - E) with S = (S0 u^i) d^(n-i), binom_vanilla_amer.cpp:33. The reference takes
+          // max(continuation, max(cp*(S - E), 0)); the continuation value is >= 0 whenever p, q >= 0 (the host sends
+          // lattices with a negative probability to tree_steps_kernel), so the inner max with 0 changes nothing.
 #pragma unroll
-          for (int j = 0; j < kR; ++j) {
-            const double c = fma(a.sgn, __dmul_rn(A[j], W[(ss + j) % kR]), a.nE);  // binom_vanilla_amer.cpp:33-35
-            sij[j] = c > 0.0 ? c : 0.0;
-          }
+          for (int j = 0; j < kR; ++j) ex[j] = fma(sgn, __dmul_rn(A[j], W[(ss + j) % kR]), nE);
         }
 #pragma unroll
         for (int j = 0; j < kR; ++j) x[j] = fma(-q0[j], a.R, x[j]);
@@ -235,9 +236,8 @@ __global__ void __launch_bounds__(kW * 32) tree_cta_kernel(TreeArgs a) {
         for (int j = 0; j < kR; ++j) v[j] = fma(x[j], a.z, q0[j]);
         if (kAmer) {
 #pragma unroll
-          for (int j = 0; j < kR; ++j) v[j] = (v[j] < sij[j]) ? sij[j] : v[j];
-          const int k = kbase - (s + kR);  // entry t = s + kR replaces t = s
-          W[ss % kR] = (k >= 0) ? s_pd[k + (k >> 4)] : 0.0;
+          for (int j = 0; j < kR; ++j) v[j] = (v[j] < ex[j]) ? ex[j] : v[j];  // std::max(jatk, sij), :34-35
+          W[ss % kR] = wp[-(s + kR)];  // entry t = s + kR replaces t = s
         }
       }
     }
@@ -339,19 +339,20 @@ static const CtaCandidate kCtaShapes[] = {
 
 // Shape of the launch that starts at an n0-node layer. The table is MEASURED (tests/tune_tree4.py: T(N) of every pinned
 // shape on a grid of N; the slope between two grid points is the cost of one layer at that width; the cheapest shape
-// per interval is listed, profiles/r1p_tune_tree_shapes.log) on a 148-SM B200 and scaled by the SM count. What it
+// per interval is listed, profiles/r1r_tune_tree_shapes.log) on a 148-SM B200 and scaled by the SM count. What it
 // encodes: (1) ptxas interleaves the independent node chains of a lane for kR <= 4 but serialises them for kR >= 6
 // (one scratch register pair per node), so more than four nodes per lane only pay when the layer is many waves wide;
 // (2) the FP64 pipe interleaves the chains of ONE warp better than those of several warps (tests/ubench: 8 warps x 1
 // chain 3.0 cycles per instruction, 1 warp x 4 chains 2.2), so the European tree prefers one kR = 4 warp per
-// sub-partition; (3) the American node needs twice the registers and its kR = 4 schedule is poorer, so it prefers
-// kR = 2 with more warps until the layer is wider than one wave.
+// sub-partition; (3) the American node carries three more values per node (S0 u^i, the d-power window, the exercise
+// value) and prefers kR = 2 with 8-16 warps until the layer is wider than one wave; (4) 256 layers per launch pay
+// only while the layer is narrow (the CTA's decaying edge is a larger share of a small CTA).
 struct ShapeRule { long long n_max; int kR, kW, kKsel; };
 static const ShapeRule kRulesEur[] = {{30000, 4, 4, 256}, {50000, 4, 4, 0}, {60000, 3, 8, 256}, {80000, 3, 8, 0},
                                       {300000, 4, 4, 0}, {-1, 4, 8, 0}};
 static const ShapeRule kRulesAmer[] = {{30000, 2, 8, 256}, {50000, 2, 8, 0}, {60000, 2, 12, 256}, {80000, 2, 12, 0},
-                                       {100000, 2, 8, 0}, {150000, 3, 12, 0}, {300000, 6, 4, 0}, {500000, 4, 12, 0},
-                                       {-1, 6, 8, 0}};
+                                       {100000, 2, 16, 0}, {125000, 3, 12, 0}, {150000, 3, 8, 0}, {200000, 6, 4, 0},
+                                       {250000, 4, 8, 0}, {400000, 6, 4, 0}, {500000, 4, 16, 0}, {-1, 6, 8, 0}};
 
 static const CtaCandidate* tree_find_shape(int kR, int kW, int kKsel) {
   for (const CtaCandidate& s : kCtaShapes)
@@ -453,8 +454,17 @@ int run_binom_tree(Ctx& c, const pcf_params& p, bool american) {
   // <warps per CTA, two digits>[<layers per launch / 64>] pins one CTA shape (e.g. 1216, 14044); PCF_TREE=<nodes per lane><layers per launch / 8> selects the warp-trapezoid
   // kernel of the first build
   const char* e = getenv("PCF_TREE");
-  if (!e) return tree_launch_cta(c, a, N, american, buf0, buf1, 0, 0, 0);
+  // tree_cta_kernel's American node relies on continuation values >= 0, i.e. on p, q >= 0; a lattice whose rounded
+  // probabilities leave [0, 1] (p is within an ulp of 0 or 1 when sigma -> 0) runs the warp kernel, which keeps both maxima
+  const bool cta_ok = !american || (pp >= 0.0 && q >= 0.0);
+  if (!e && cta_ok) return tree_launch_cta(c, a, N, american, buf0, buf1, 0, 0, 0);
+  if (!e) return N > 250000 ? tree_launch_all<4, 32>(c, a, N, american, buf0, buf1)
+                            : tree_launch_all<4, 64>(c, a, N, american, buf0, buf1);
   const int shape = atoi(e);
+  if (shape >= 1000 && shape < 20000 && !cta_ok) {
+    set_last_error("PCF_TREE: the CTA kernel needs p, q >= 0 for the American tree");
+    return PCF_EINVAL;
+  }
   if (shape >= 1000 && shape < 2000) return tree_launch_cta(c, a, N, american, buf0, buf1, (shape / 100) % 10, shape % 100, 0);
   if (shape >= 10000 && shape < 20000)
     return tree_launch_cta(c, a, N, american, buf0, buf1, (shape / 1000) % 10, (shape / 10) % 100, 64 * (shape % 10));

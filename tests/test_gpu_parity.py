@@ -353,6 +353,14 @@ def test_trees_launch_shape_independence_and_properties(gpu, monkeypatch):
         for pf in ("call", "put"):
             assert gpu.binom_vanilla_eur(*P, N, pf).price == oracle.binom_tree(*P, N, pf, False)
             assert gpu.binom_vanilla_amer(*P, N, pf).price == oracle.binom_tree(*P, N, pf, True)
+    # lattices whose rounded probabilities leave [0, 1] (sigma -> 0): the CTA kernel's single max would differ from the
+    # reference's max(continuation, max(payoff, 0)), so the host routes them to the warp kernel -- still bit-equal
+    for r_, sig_, N in ((0.1, 1e-7, 1000), (-0.05, 1e-7, 100)):
+        for pf in ("call", "put"):
+            for E_ in (100, 95, 105):
+                Pq = (100, E_, r_, sig_, 1)
+                assert gpu.binom_vanilla_amer(*Pq, N, pf).price == oracle.binom_tree(*Pq, N, pf, True), (Pq, N, pf)
+                assert gpu.binom_vanilla_eur(*Pq, N, pf).price == oracle.binom_tree(*Pq, N, pf, False), (Pq, N, pf)
     # wide trees walk every rule of the per-launch shape table (csrc/tree_kernels.cu: tree_pick_shape)
     N = 600_000
     auto = (gpu.binom_vanilla_eur(*P, N, "put").price, gpu.binom_vanilla_amer(*P, N, "put").price)
