@@ -26,6 +26,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <thread>
+#include <type_traits>
 #include <vector>
 #include "common.cuh"
 #include "binom_math.cuh"
@@ -141,6 +142,16 @@ __global__ void __launch_bounds__(kTreeWarps * 32) tree_steps_kernel(TreeArgs a)
   }
 }
 
+// f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{}): a loop whose index is a constant
+// expression inside the body
+template <int N, int I = 0, typename F>
+__device__ __forceinline__ void unrolled(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    unrolled<N, I + 1>(f);
+  }
+}
+
 // CTA-cooperative trapezoid (see the header). Geometry, all in CTA-local node positions c = warp*kOwn + lane*kR + j:
 //   kL = 32 kR nodes per warp, kOwn = kL - kH of them owned, kC = kW kOwn + kH nodes per CTA; after s layers the
 //   positions [0, kC - s) are exact, so a launch of a.steps <= kK layers finishes a.stride = kC - kK of them.
@@ -206,41 +217,49 @@ __global__ void __launch_bounds__(kW * 32) tree_cta_kernel(TreeArgs a) {
 #pragma unroll
     for (int t = 0; t < kR; ++t) W[t] = wp[-t];
   }
-  const int rounds = (a.steps + kH - 1) / kH;
-  for (int r = 0; r < rounds; ++r) {
+  // One layer (s = r kH + ss; kH % kR == 0, so s % kR == ss % kR and the register indices are static).
+  // The kR nodes of a lane are independent within a layer. Written node by node, ptxas keeps each node's
+  // six-instruction dependent chain contiguous (one scratch register pair, kR x 48 cycles per layer); written
+  // stage by stage it issues the kR chains interleaved, which is what keeps the FP64 pipe busy.
+  auto layer = [&](int s, auto ss_tag) {
+    constexpr int ss = decltype(ss_tag)::value;
+    const double halo = __shfl_down_sync(0xffffffffu, v[0], 1);  // lane 31: the warp's halo decays by one node
+    double x[kR], q0[kR], ex[kR];
 #pragma unroll
-    for (int ss = 0; ss < kH; ++ss) {  // kH % kR == 0, so (r kH + ss) % kR == ss % kR: register indices are static
-      const int s = r * kH + ss;
-      if (s < a.steps) {  // block-uniform
-        const double halo = __shfl_down_sync(0xffffffffu, v[0], 1);  // lane 31: the warp's halo decays by one node
-        // The kR nodes of a lane are independent within a layer. Written node by node, ptxas keeps each node's
-        // six-instruction dependent chain contiguous (one scratch register pair, kR x 48 cycles per layer); written
-        // stage by stage it issues the kR chains interleaved, which is what keeps the FP64 pipe busy.
-        double x[kR], q0[kR], ex[kR];
+    for (int j = 0; j < kR; ++j) x[j] = __dmul_rn(a.q, v[j]);
 #pragma unroll
-        for (int j = 0; j < kR; ++j) x[j] = __dmul_rn(a.q, v[j]);
+    for (int j = 0; j < kR; ++j) x[j] = __dadd_rn(__dmul_rn(a.p, (j + 1 < kR) ? v[j + 1] : halo), x[j]);
 #pragma unroll
-        for (int j = 0; j < kR; ++j) x[j] = __dadd_rn(__dmul_rn(a.p, (j + 1 < kR) ? v[j + 1] : halo), x[j]);
+    for (int j = 0; j < kR; ++j) q0[j] = __dmul_rn(x[j], a.z);
+    if (kAmer) {
+      // cp*(S - E) with S = (S0 u^i) d^(n-i), binom_vanilla_amer.cpp:33. The reference takes
+      // max(continuation, max(cp*(S - E), 0)); the continuation value is >= 0 whenever p, q >= 0 (the host sends
+      // lattices with a negative probability to tree_steps_kernel), so the inner max with 0 changes nothing.
 #pragma unroll
-        for (int j = 0; j < kR; ++j) q0[j] = __dmul_rn(x[j], a.z);
-        if (kAmer) {
-          // cp*(S - E) with S = (S0 u^i) d^(n-i), binom_vanilla_amer.cpp:33. The reference takes
-          // max(continuation, max(cp*(S - E), 0)); the continuation value is >= 0 whenever p, q >= 0 (the host sends
-          // lattices with a negative probability to tree_steps_kernel), so the inner max with 0 changes nothing.
-#pragma unroll
-          for (int j = 0; j < kR; ++j) ex[j] = fma(sgn, __dmul_rn(A[j], W[(ss + j) % kR]), nE);
-        }
-#pragma unroll
-        for (int j = 0; j < kR; ++j) x[j] = fma(-q0[j], a.R, x[j]);
-#pragma unroll
-        for (int j = 0; j < kR; ++j) v[j] = fma(x[j], a.z, q0[j]);
-        if (kAmer) {
-#pragma unroll
-          for (int j = 0; j < kR; ++j) v[j] = (v[j] < ex[j]) ? ex[j] : v[j];  // std::max(jatk, sij), :34-35
-          W[ss % kR] = wp[-(s + kR)];  // entry t = s + kR replaces t = s
-        }
-      }
+      for (int j = 0; j < kR; ++j) ex[j] = fma(sgn, __dmul_rn(A[j], W[(ss + j) % kR]), nE);
     }
+#pragma unroll
+    for (int j = 0; j < kR; ++j) x[j] = fma(-q0[j], a.R, x[j]);
+#pragma unroll
+    for (int j = 0; j < kR; ++j) v[j] = fma(x[j], a.z, q0[j]);
+    if (kAmer) {
+#pragma unroll
+      for (int j = 0; j < kR; ++j) v[j] = (v[j] < ex[j]) ? ex[j] : v[j];  // std::max(jatk, sij), :34-35
+      W[ss % kR] = wp[-(s + kR)];  // entry t = s + kR replaces t = s
+    }
+  };
+  // kH layers back to back. Full rounds carry no per-layer test, so a round is ONE basic block and the scheduler can
+  // start the shuffle-independent nodes of layer s+1 under the tail of layer s; only the last, partial round tests.
+  auto round_of = [&](int r, auto guarded) {
+    unrolled<kH>([&](auto ss_tag) {
+      const int s = r * kH + decltype(ss_tag)::value;
+      if (!decltype(guarded)::value || s < a.steps) layer(s, ss_tag);  // block-uniform
+    });
+  };
+  const int rounds = (a.steps + kH - 1) / kH, full = a.steps / kH;
+  for (int r = 0; r < rounds; ++r) {
+    if (r < full) round_of(r, std::false_type{});
+    else round_of(r, std::true_type{});
     if (r + 1 < rounds) {  // refill every warp's halo from its right neighbour's first kH nodes
       if (lane < kHaloLanes) {
 #pragma unroll
@@ -339,7 +358,7 @@ static const CtaCandidate kCtaShapes[] = {
 
 // Shape of the launch that starts at an n0-node layer. The table is MEASURED (tests/tune_tree4.py: T(N) of every pinned
 // shape on a grid of N; the slope between two grid points is the cost of one layer at that width; the cheapest shape
-// per interval is listed, profiles/r1r_tune_tree_shapes.log) on a 148-SM B200 and scaled by the SM count. What it
+// per interval is listed, profiles/r1s_tune_tree_shapes.log) on a 148-SM B200 and scaled by the SM count. What it
 // encodes: (1) ptxas interleaves the independent node chains of a lane for kR <= 4 but serialises them for kR >= 6
 // (one scratch register pair per node), so more than four nodes per lane only pay when the layer is many waves wide;
 // (2) the FP64 pipe interleaves the chains of ONE warp better than those of several warps (tests/ubench: 8 warps x 1
@@ -349,10 +368,11 @@ static const CtaCandidate kCtaShapes[] = {
 // only while the layer is narrow (the CTA's decaying edge is a larger share of a small CTA).
 struct ShapeRule { long long n_max; int kR, kW, kKsel; };
 static const ShapeRule kRulesEur[] = {{30000, 4, 4, 256}, {50000, 4, 4, 0}, {60000, 3, 8, 256}, {80000, 3, 8, 0},
+                                      {100000, 4, 4, 0}, {125000, 4, 8, 0}, {200000, 4, 4, 0}, {250000, 4, 8, 0},
                                       {300000, 4, 4, 0}, {-1, 4, 8, 0}};
-static const ShapeRule kRulesAmer[] = {{30000, 2, 8, 256}, {50000, 2, 8, 0}, {60000, 2, 12, 256}, {80000, 2, 12, 0},
-                                       {100000, 2, 16, 0}, {125000, 3, 12, 0}, {150000, 3, 8, 0}, {200000, 6, 4, 0},
-                                       {250000, 4, 8, 0}, {400000, 6, 4, 0}, {500000, 4, 16, 0}, {-1, 6, 8, 0}};
+static const ShapeRule kRulesAmer[] = {{30000, 2, 8, 256}, {50000, 2, 8, 0}, {60000, 3, 8, 256}, {80000, 2, 12, 0},
+                                       {90000, 6, 4, 0}, {100000, 2, 16, 0}, {125000, 4, 8, 0}, {150000, 3, 8, 0},
+                                       {200000, 6, 4, 0}, {250000, 4, 8, 0}, {700000, 6, 4, 0}, {-1, 6, 8, 0}};
 
 static const CtaCandidate* tree_find_shape(int kR, int kW, int kKsel) {
   for (const CtaCandidate& s : kCtaShapes)
