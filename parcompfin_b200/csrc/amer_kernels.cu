@@ -51,7 +51,7 @@ struct AmerArgs {
   long long Np;       // padded row length (multiple of 4)
   unsigned long long seed;
   const double* w;    // replay: w[(p-p0)*M + (m-1)]
-  int dbg;            // PCF_AMER_DBG & 16: timing experiment, only the last row is stored (results are wrong)
+  int dbg;            // PCF_AMER_DBG: experiment bits of the sweep kernels (none in the path kernel)
 };
 
 // a6: antithetic pairs, S+ and S- in registers, one Philox block per two dates, kPairs pairs per thread.
@@ -123,7 +123,34 @@ __global__ void __launch_bounds__(kAmerBlock, kMinBlocks) amer_paths_kernel(Amer
         }
       }
     } else {
-      for (int m = 1; m <= a.M; m += 2) {
+      // Two dates per Philox block. The loop body carries no test on m, so it is ONE basic block in which ptxas runs
+      // the kPairs Philox / Box-Muller chains side by side (with a per-date test every pair was its own block and its
+      // dependent chain ran alone: 10.2 ms instead of the 7.4 ms the FP64 pipe needs at 1e8 x 50); an odd M ends
+      // with one single-date step.
+      int m = 1;
+      for (; m + 1 <= a.M; m += 2) {
+        double z0[kPairs], z1[kPairs];
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+          const uint64_t g = (uint64_t)(a.p0 + pp[q]);
+          uint32_t x[4];
+          philox4x32_10(key, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)((m - 1) >> 1), PCF_STREAM_AMER, x);
+          box_muller_pair(x, tv, hc, z0[q], z1[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+          amer_step(Sp[q], Sm[q], z0[q], cs, my_T);
+          __stcs(paths + (size_t)(m - 1) * Np + pp[q], Sp[q]);
+          __stcs(paths + (size_t)(m - 1) * Np + pp[q] + a.H, Sm[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+          amer_step(Sp[q], Sm[q], z1[q], cs, my_T);
+          __stcs(paths + (size_t)m * Np + pp[q], Sp[q]);
+          __stcs(paths + (size_t)m * Np + pp[q] + a.H, Sm[q]);
+        }
+      }
+      if (m <= a.M) {
 #pragma unroll
         for (int q = 0; q < kPairs; ++q) {
           const uint64_t g = (uint64_t)(a.p0 + pp[q]);
@@ -132,17 +159,8 @@ __global__ void __launch_bounds__(kAmerBlock, kMinBlocks) amer_paths_kernel(Amer
           double z0, z1;
           box_muller_pair(x, tv, hc, z0, z1);
           amer_step(Sp[q], Sm[q], z0, cs, my_T);
-          if (!(a.dbg & 16) || m == a.M) {
-            __stcs(paths + (size_t)(m - 1) * Np + pp[q], Sp[q]);
-            __stcs(paths + (size_t)(m - 1) * Np + pp[q] + a.H, Sm[q]);
-          }
-          if (m + 1 <= a.M) {
-            amer_step(Sp[q], Sm[q], z1, cs, my_T);
-            if (!(a.dbg & 16) || m + 1 == a.M) {
-              __stcs(paths + (size_t)m * Np + pp[q], Sp[q]);
-              __stcs(paths + (size_t)m * Np + pp[q] + a.H, Sm[q]);
-            }
-          }
+          __stcs(paths + (size_t)(m - 1) * Np + pp[q], Sp[q]);
+          __stcs(paths + (size_t)(m - 1) * Np + pp[q] + a.H, Sm[q]);
         }
       }
     }
@@ -652,7 +670,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   } else {
     // launch shape: PCF_AMER_GEN = <pairs per thread><CTAs per SM> (tuning knob)
     const char* v = getenv("PCF_AMER_GEN");
-    const int variant = v ? atoi(v) : 22;
+    const int variant = v ? atoi(v) : 32;  // ncu, 1e8 x 50: 32 -> 9.1 ms, 22 -> 9.6, 23 -> 9.9, 14 -> 10.5
 #define PCF_GEN_CASE(P, B)                                                                       \
   case P * 10 + B: {                                                                             \
     int grid_gen = grid_for(c, (H + P - 1) / P, kAmerBlock, B);                                  \

@@ -181,6 +181,8 @@ mc_asia_kernel(AsiaArgs a, const MathTables* __restrict__ tables, PeerLink link,
       hi[p] = (uint32_t)((uint64_t)n >> 32);
     }
     int m = 0;
+    // (unrolling this loop 2x / 3x so that consecutive date pairs share a basic block is slower at 6 paths per thread --
+    // 706 -> 778 / 821 ms, the body already needs 250 registers -- and 4 paths x 2 only ties: profiles/r1s_tune_asia_unroll.log)
     for (; m + 1 < a.M; m += 2) {
 #pragma unroll
       for (int p = 0; p < kPaths; ++p) {
@@ -322,7 +324,10 @@ struct BasketArgs {
 // kFull: the normal transform is a full matrix (eigen-decomposition fallback of mvn.h:72-76), not a lower triangle.
 // kPaths paths per thread iteration: their Philox / Box-Muller chains are independent instruction streams in one loop
 // body, which is what keeps the FP64 pipe fed with one CTA per SM (same finding as mc_asia_kernel, profiles/r1_notes.md).
-template <int D, bool kReplay, bool kFull, int kPaths, int kMinB>
+// kExact: a.d == D, so the per-column and per-asset tests on a.d are compile-time true and the whole path is ONE basic
+// block: ptxas can then run the eight Philox / Box-Muller chains and the sixteen exponentials side by side instead of
+// one (dependent) chain per block (same finding as the tree kernel's guard-free rounds, profiles/r1_notes.md).
+template <int D, bool kReplay, bool kFull, int kPaths, int kMinB, bool kExact = false>
 __global__ void __launch_bounds__(kBlock, kMinB) mc_basket_kernel(BasketArgs a, const MathTables* __restrict__ tables,
                                                            PeerLink link, double* partials, unsigned int* ticket,
                                                            double* out) {
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(kBlock, kMinB) mc_basket_kernel(BasketArgs a, 
     // column sweep of the triangular product: z_k is consumed as soon as it is drawn
 #pragma unroll
     for (int j = 0; j < D / 2 + (D & 1); ++j) {
-      if (2 * j < a.d) {
+      if (kExact || 2 * j < a.d) {
         double z0[kPaths], z1[kPaths];
 #pragma unroll
         for (int q = 0; q < kPaths; ++q) {
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(kBlock, kMinB) mc_basket_kernel(BasketArgs a, 
       double basket = 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i)
-        if (i < a.d) basket = fma(c_bw[i], exp_table_pinned(bt[q][i], tv, xmagic, xe5), basket);  // :30
+        if (kExact || i < a.d) basket = fma(c_bw[i], exp_table_pinned(bt[q][i], tv, xmagic, xe5), basket);  // :30
       double v = payoff(basket, a.E, a.cp);
       if (kPaths > 1 && nb + q * stride >= a.n1) v = 0.0;
       t1 += v;
@@ -476,11 +481,18 @@ static int launch_basket(Ctx& c, const BasketArgs& a, long long paths, bool repl
                           : basket_launch(c, mc_basket_kernel<D, true, false, 1, 3>, a, paths, 1, link);
   const char* e = getenv("PCF_BASKET_GEN");
   const int shape = e ? atoi(e) : 13;
-#define PCF_BG(P, B) (full ? basket_launch(c, mc_basket_kernel<D, false, true, P, B>, a, paths, P, link) \
-                           : basket_launch(c, mc_basket_kernel<D, false, false, P, B>, a, paths, P, link))
+  const bool exact = a.d == D && !getenv("PCF_BASKET_GUARDED");  // A/B knob: keep the per-column tests
+#define PCF_BG(P, B)                                                                                              \
+  (exact ? (full ? basket_launch(c, mc_basket_kernel<D, false, true, P, B, true>, a, paths, P, link)              \
+                 : basket_launch(c, mc_basket_kernel<D, false, false, P, B, true>, a, paths, P, link))            \
+         : (full ? basket_launch(c, mc_basket_kernel<D, false, true, P, B>, a, paths, P, link)                    \
+                 : basket_launch(c, mc_basket_kernel<D, false, false, P, B>, a, paths, P, link)))
   switch (shape) {
     case 13: return PCF_BG(1, 3);
+    case 12: return PCF_BG(1, 2);
+    case 11: return PCF_BG(1, 1);
     case 21: return PCF_BG(2, 1);
+    case 22: return PCF_BG(2, 2);
     default:
       set_last_error("unknown PCF_BASKET_GEN");
       return PCF_EINVAL;
