@@ -92,7 +92,10 @@ int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay,
       PCF_EUR_CASE(2, 2)
       PCF_EUR_CASE(2, 3)
       PCF_EUR_CASE(3, 2)
+      PCF_EUR_CASE(3, 3)
       PCF_EUR_CASE(4, 1)
+      PCF_EUR_CASE(4, 2)
+      PCF_EUR_CASE(5, 1)
       PCF_EUR_CASE(6, 1)
       PCF_EUR_CASE(8, 1)
       default:
@@ -471,7 +474,8 @@ static int basket_launch(Ctx& c, K kernel, const BasketArgs& a, long long paths,
   return PCF_OK;
 }
 
-// Launch shape of the native kernel: PCF_BASKET_GEN = <paths per thread><CTAs per SM> (tuning knob): 13 (default) | 21.
+// Launch shape of the native kernel: PCF_BASKET_GEN = <paths per thread><CTAs per SM> (tuning knob): 13, 12, 11, 21, 22
+// (default 12 for the guard-free instantiation, 13 otherwise).
 // Measured at d = 16, 1e9 paths (profiles/r1_notes.md): 13 -> 82 ms, 22 -> 88 ms, 41 -> 92 ms, 21 -> 102 ms: unlike the
 // Asian and equicorrelation kernels this one prefers warps to paths per thread (its 136 factor entries are used once per
 // path and already crowd the uniform register file). The replay flavour (parity path) is built once.
@@ -480,8 +484,8 @@ static int launch_basket(Ctx& c, const BasketArgs& a, long long paths, bool repl
   if (replay) return full ? basket_launch(c, mc_basket_kernel<D, true, true, 1, 3>, a, paths, 1, link)
                           : basket_launch(c, mc_basket_kernel<D, true, false, 1, 3>, a, paths, 1, link);
   const char* e = getenv("PCF_BASKET_GEN");
-  const int shape = e ? atoi(e) : 13;
   const bool exact = a.d == D && !getenv("PCF_BASKET_GUARDED");  // A/B knob: keep the per-column tests
+  const int shape = e ? atoi(e) : (exact ? 12 : 13);  // one-block body: 1 path x 2 CTAs/SM (126 registers) is fastest
 #define PCF_BG(P, B)                                                                                              \
   (exact ? (full ? basket_launch(c, mc_basket_kernel<D, false, true, P, B, true>, a, paths, P, link)              \
                  : basket_launch(c, mc_basket_kernel<D, false, false, P, B, true>, a, paths, P, link))            \

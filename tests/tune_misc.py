@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import parcompfin_b200 as pcf
 pcf.init(1)
 a = (100., 100., .05, .2, 1.)
-for v in "14,22,23,32,41,61,81".split(","):
+for v in "14,22,23,32,33,41,42,51,61,81".split(","):
     os.environ["PCF_EUR_VARIANT"] = v
     best = 0
     for i in range(3):
