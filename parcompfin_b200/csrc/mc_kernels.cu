@@ -36,8 +36,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) mc_eur_kernel(EurArgs a, c
   const PhiloxKey key(a.seed);
   Comp s1, s2;
   const long long T = (long long)gridDim.x * blockDim.x;
-  const double S0 = a.S0, E = a.E, sig = kReplay ? a.sigma : a.sigma * a.sqrtT, drift = a.drift;
-  const int cp = a.cp;
+  const double S0 = a.S0, sig = kReplay ? a.sigma : a.sigma * a.sqrtT, drift = a.drift;
+  const double sgn = (double)a.cp, nE = -sgn * a.E;  // cp*(S - E) = fma(sgn, S, nE): the same rounding as (double)cp*(S - E)
   for (long long base = a.k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; base < a.k1; base += T * kPairs) {
     double t1 = 0.0, t2 = 0.0;
 #pragma unroll
@@ -51,8 +51,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) mc_eur_kernel(EurArgs a, c
       } else {
         normal_pair(key, (uint64_t)k, 0u, PCF_STREAM_EUR, tv, hc, w0, w1);  // sqrt(T) folded into `sig`
       }
-      double v0 = payoff(S0 * exp_any<kSmallExp>(fma(sig, w0, drift), tv, hc), E, cp);  // mc_eur.cpp:24
-      double v1 = payoff(S0 * exp_any<kSmallExp>(fma(sig, w1, drift), tv, hc), E, cp);
+      // payoff (mc_eur.cpp:24) carried DOUBLED: 2 max(t, 0) = t + |t| is one DADD (|.| is an operand modifier) where
+      // max costs a DSETP and two FSELs; the sums are scaled back by 1/2 and 1/4 below -- exact, so bit-identical
+      const double u0 = fma(sgn, S0 * exp_any<kSmallExp>(fma(sig, w0, drift), tv, hc), nE);
+      const double u1 = fma(sgn, S0 * exp_any<kSmallExp>(fma(sig, w1, drift), tv, hc), nE);
+      double v0 = u0 + fabs(u0), v1 = u1 + fabs(u1);
       v0 = has1 ? v0 : 0.0;
       v1 = has2 ? v1 : 0.0;
       t1 += v0 + v1;
@@ -61,6 +64,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) mc_eur_kernel(EurArgs a, c
     s1.add(t1);
     s2.add(t2);
   }
+  s1.hi *= 0.5;  s1.lo *= 0.5;
+  s2.hi *= 0.25; s2.lo *= 0.25;
   Comp v[2] = {s1, s2};
   grid_reduce<2>(v, smem, partials, ticket, out, &link);
 }
