@@ -427,15 +427,19 @@ static int tree_launch_cta(Ctx& c, TreeArgs a, long long N, bool amer, double* b
 }
 
 // pow tables with the reference's own libm call, spread over the host's cores (2(N+1) calls; a serial loop would
-// cost as much as the whole device computation at N = 1e5)
-static void pow_table(double base, long long N, double* out) {
-  unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+// cost as much as the whole device computation at N = 1e5). One set of threads fills both tables.
+static void pow_tables(double u, double d, long long N, double* out_u, double* out_d) {
+  unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   if (N < 4096) nt = 1;
+  auto work = [=](unsigned t) {
+    for (long long i = t; i <= N; i += nt) {
+      out_u[i] = pow(u, (double)(int)i);  // pow(u,i): i is an int in the reference
+      out_d[i] = pow(d, (double)(int)i);
+    }
+  };
   std::vector<std::thread> th;
-  for (unsigned t = 0; t < nt; ++t)
-    th.emplace_back([=] {
-      for (long long i = t; i <= N; i += nt) out[i] = pow(base, (double)(int)i);  // pow(u,i): i is an int in the reference
-    });
+  for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
   for (auto& x : th) x.join();
 }
 
@@ -457,8 +461,7 @@ int run_binom_tree(Ctx& c, const pcf_params& p, bool american) {
   double* buf0 = (double*)(ws + 2 * slot);
   double* buf1 = (double*)(ws + 3 * slot);
   std::vector<double> h(2 * (size_t)(N + 1));
-  pow_table(u, N, h.data());
-  pow_table(d, N, h.data() + (N + 1));
+  pow_tables(u, d, N, h.data(), h.data() + (N + 1));
   PCF_CUDA(cudaMemcpyAsync(d_pu, h.data(), (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, c.stream));
   PCF_CUDA(cudaMemcpyAsync(d_pd, h.data() + (N + 1), (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, c.stream));
   PCF_CUDA(cudaStreamSynchronize(c.stream));  // `h` dies with this frame
