@@ -21,6 +21,12 @@ for N in (1, 2, 1001, 300_000):
     print("binom", N, pcf.binom(*P, N, "call").price, pcf.binom(*P, N, "put", screen=False).price)
 for N in (1, 63, 64, 65, 1000, 5000):
     print("trees", N, pcf.binom_vanilla_eur(*P, N, "put").price, pcf.binom_vanilla_amer(*P, N, "put").price)
+for shape in ("1216", "1312", "1404", "14044", "1604", "48"):  # pinned CTA shapes (halo exchange), the warp kernel
+    os.environ["PCF_TREE"] = shape
+    print("trees", shape, pcf.binom_vanilla_eur(*P, 3001, "put").price, pcf.binom_vanilla_amer(*P, 3001, "put").price)
+os.environ.pop("PCF_TREE")
+print("basket general d=16 (guard-free body)", pcf.mc_basket(100, 100, .05, .2, 1, 20_001, "call", 16,
+                                                           cov=.5 * np.eye(16) + .5, seed=1).price)
 print("stream", pcf.normal_stream(3, 1, 0, 100, 5).sum(), pcf.philox4x32_10((0, 0, 0, 0), (0, 0)))
 pcf.shutdown()
 print("done")
