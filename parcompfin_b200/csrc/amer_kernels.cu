@@ -51,7 +51,6 @@ struct AmerArgs {
   long long Np;       // padded row length (multiple of 4)
   unsigned long long seed;
   const double* w;    // replay: w[(p-p0)*M + (m-1)]
-  int dbg;            // PCF_AMER_DBG: experiment bits of the sweep kernels (none in the path kernel)
 };
 
 // a6: antithetic pairs, S+ and S- in registers, one Philox block per two dates, kPairs pairs per thread.
@@ -651,7 +650,6 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   a.adt = (p.r - 0.5 * p.sigma * p.sigma) * dt;
   a.cs = d_replay ? p.sigma : p.sigma * sqrt(dt);
   a.p0 = pairs.begin; a.H = H; a.Np = Np; a.seed = p.seed; a.w = d_replay;
-  a.dbg = getenv("PCF_AMER_DBG") ? atoi(getenv("PCF_AMER_DBG")) : 0;
 
   {
     // per-call table: e^a 2^(+-j/32), a = (r - sigma^2/2) dt, in long double then rounded once
