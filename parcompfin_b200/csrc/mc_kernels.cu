@@ -479,11 +479,11 @@ static int basket_launch(Ctx& c, K kernel, const BasketArgs& a, long long paths,
   return PCF_OK;
 }
 
-// Launch shape of the native kernel: PCF_BASKET_GEN = <paths per thread><CTAs per SM> (tuning knob): 13, 12, 11, 21, 22
-// (default 12 for the guard-free instantiation, 13 otherwise).
-// Measured at d = 16, 1e9 paths (profiles/r1_notes.md): 13 -> 82 ms, 22 -> 88 ms, 41 -> 92 ms, 21 -> 102 ms: unlike the
-// Asian and equicorrelation kernels this one prefers warps to paths per thread (its 136 factor entries are used once per
-// path and already crowd the uniform register file). The replay flavour (parity path) is built once.
+// Launch shape of the native kernel: PCF_BASKET_GEN = <paths per thread><CTAs per SM> (tuning knob): 13 | 12.
+// Measured at d = 16 (profiles/r1_notes.md, r1s_tune_basket_general.log). Guarded body, 1e9 paths: 13 -> 82 ms, 22 -> 88,
+// 41 -> 92, 21 -> 102. Guard-free body (kExact), 2e8 paths: 12 -> 12.2 ms, 22 -> 12.2, 21 -> 12.4, 13 -> 12.9, 11 -> 14.4
+// (guarded 13: 16.4). Default 12 for the guard-free instantiation, 13 otherwise; only these two are built (every shape
+// costs 20 instantiations). The replay flavour (parity path) is built once per dimension.
 template <int D>
 static int launch_basket(Ctx& c, const BasketArgs& a, long long paths, bool replay, bool full, const PeerLink& link) {
   if (replay) return full ? basket_launch(c, mc_basket_kernel<D, true, true, 1, 3>, a, paths, 1, link)
@@ -499,9 +499,7 @@ static int launch_basket(Ctx& c, const BasketArgs& a, long long paths, bool repl
   switch (shape) {
     case 13: return PCF_BG(1, 3);
     case 12: return PCF_BG(1, 2);
-    case 11: return PCF_BG(1, 1);
-    case 21: return PCF_BG(2, 1);
-    case 22: return PCF_BG(2, 2);
+    // (11, 21 and 22 were measured too, profiles/r1s_tune_basket_general.log; not built: 70 instantiations cost minutes)
     default:
       set_last_error("unknown PCF_BASKET_GEN");
       return PCF_EINVAL;

@@ -13,7 +13,7 @@ for guarded in ("1", None):
     os.environ.pop("PCF_BASKET_GUARDED", None)
     if guarded:
         os.environ["PCF_BASKET_GUARDED"] = guarded
-    for shape in ("13", "12", "11", "21", "22"):
+    for shape in ("13", "12"):
         os.environ["PCF_BASKET_GEN"] = shape
         best = None
         for i in range(3):
