@@ -183,3 +183,39 @@ def test_compiled_reference_still_agrees():
     w = oracle.normals_mt19937(77, math.sqrt(1 / M), N // 2 * M)
     assert rel(oracle.mc_amer(100, 100, .05, .2, 1, N, M, "put", w),
                oracle.ref_fn("mc_amer", "put", 100, 100, .05, .2, 1, N, M, seed=77)) < 1e-15
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (reference absent)")
+def test_restatement_equals_compiled_reference_on_random_parameters():
+    # Beyond the committed golden vectors: 40 seeded random parameter sets per method, restatement vs the compiled,
+    # unmodified reference fed the same mt19937 stream -- bit-equal for the Monte Carlo methods and the trees, and to the
+    # reference's own accuracy for the binomial formula (its comb() drifts).
+    import numpy as np
+    rng = np.random.default_rng(20240229)
+    for k in range(40):
+        S0 = float(rng.uniform(50, 150)); E = float(rng.uniform(50, 150))
+        r = float(rng.uniform(0.0, 0.1)); sigma = float(rng.uniform(0.05, 0.8)); T = float(rng.uniform(0.25, 3.0))
+        pf = "call" if k % 2 else "put"
+        seed = int(rng.integers(1, 10**6))
+        N = int(rng.integers(2, 300)) * 2
+        M = int(rng.integers(2, 40))
+        w = oracle.normals_mt19937(seed, math.sqrt(T), N)
+        assert oracle.mc_eur(S0, E, r, sigma, T, N, pf, w) == oracle.ref_fn("mc_eur", pf, S0, E, r, sigma, T, N, seed=seed)
+        w = oracle.normals_mt19937(seed, math.sqrt(T / M), N * M)
+        assert oracle.mc_asia(S0, E, r, sigma, T, N, M, pf, w) == \
+            oracle.ref_fn("mc_asia", pf, S0, E, r, sigma, T, N, M, seed=seed)
+        w = oracle.normals_mt19937(seed, math.sqrt(T / M), N // 2 * M)
+        try:
+            want = oracle.ref_fn("mc_amer", pf, S0, E, r, sigma, T, N, M, seed=seed)
+        except Exception:           # the reference aborts on a singular regression (det <= 0): so must the restatement
+            with pytest.raises(Exception):
+                oracle.mc_amer(S0, E, r, sigma, T, N, M, pf, w)
+        else:
+            assert oracle.mc_amer(S0, E, r, sigma, T, N, M, pf, w) == want
+        Nt = int(rng.integers(1, 400))
+        assert oracle.binom_tree(S0, E, r, sigma, T, Nt, pf, False) == \
+            oracle.ref_fn("binom_vanilla_eur", pf, S0, E, r, sigma, T, Nt)
+        assert oracle.binom_tree(S0, E, r, sigma, T, Nt, pf, True) == \
+            oracle.ref_fn("binom_vanilla_amer", pf, S0, E, r, sigma, T, Nt)
+        want = oracle.ref_fn("binom_embar", pf, S0, E, r, sigma, T, Nt)
+        assert rel(oracle.binom(S0, E, r, sigma, T, Nt, pf), want) < 1e-11 or abs(want) < 1e-9
