@@ -453,6 +453,44 @@ def test_edge_cases(gpu):
             assert abs(g - o) < 1e-11 * max(1, abs(o)), (N, pf)
 
 
+def test_replay_parity_on_random_parameters(gpu):
+    # Beyond the golden vectors: seeded random parameter sets, every method through the C ABI in replay mode against the
+    # oracle on the same mt19937 stream (1e-12 relative; the trees bit-equal). tests/test_oracle.py pins the oracle to
+    # the compiled reference on random sets of the same kind.
+    rng = np.random.default_rng(31415)
+    for k in range(16):
+        S0 = float(rng.uniform(60, 140)); E = float(rng.uniform(60, 140))
+        r = float(rng.uniform(0.0, 0.1)); sigma = float(rng.uniform(0.05, 0.6)); T = float(rng.uniform(0.25, 2.0))
+        pf = "call" if k % 2 else "put"
+        seed = int(rng.integers(1, 10**6))
+        N = int(rng.integers(100, 3000)) * 2
+        M = int(rng.integers(2, 60))
+        d = int(rng.integers(1, 17)); rho = float(rng.uniform(0.0, 0.9))
+        tol = lambda want: REPLAY_TOL * max(abs(want), 1e-3)
+        w = oracle.normals_mt19937(seed, math.sqrt(T), N)
+        want = oracle.mc_eur(S0, E, r, sigma, T, N, pf, w)
+        assert abs(gpu.mc_eur(S0, E, r, sigma, T, N, pf, replay=w).price - want) <= tol(want), (k, "eur")
+        w = oracle.normals_mt19937(seed, math.sqrt(T / M), N * M)
+        want = oracle.mc_asia(S0, E, r, sigma, T, N, M, pf, w)
+        assert abs(gpu.mc_asia(S0, E, r, sigma, T, N, M, pf, replay=w).price - want) <= tol(want), (k, "asia")
+        Z = oracle.normals_mt19937(seed, 1.0, N * d)
+        want = oracle.mc_basket(S0, E, r, sigma, T, N, pf, d, rho, Z)
+        assert abs(gpu.mc_eur_multi(S0, E, r, sigma, T, N, pf, d, rho, replay=Z).price - want) <= tol(want), (k, "basket", d)
+        w = oracle.normals_mt19937(seed, math.sqrt(T / M), N // 2 * M)
+        try:
+            want = oracle.mc_amer(S0, E, r, sigma, T, N, M, pf, w)
+        except Exception:   # singular regression: the reference throws (common.h:115-117), so does the library
+            with pytest.raises(ValueError):
+                gpu.mc_amer(S0, E, r, sigma, T, N, M, pf, replay=w)
+        else:
+            assert abs(gpu.mc_amer(S0, E, r, sigma, T, N, M, pf, replay=w).price - want) <= tol(want), (k, "amer")
+        Nt = int(rng.integers(1, 3000))
+        assert gpu.binom_vanilla_eur(S0, E, r, sigma, T, Nt, pf).price == oracle.binom_tree(S0, E, r, sigma, T, Nt, pf, False)
+        assert gpu.binom_vanilla_amer(S0, E, r, sigma, T, Nt, pf).price == oracle.binom_tree(S0, E, r, sigma, T, Nt, pf, True)
+        want = oracle.binom(S0, E, r, sigma, T, Nt, pf)
+        assert abs(gpu.binom(S0, E, r, sigma, T, Nt, pf).price - want) <= 1e-10 * max(abs(want), 1e-3), (k, "binom")
+
+
 def test_error_behaviour(gpu):
     with pytest.raises(ValueError, match="divisible by 2"):
         gpu.mc_amer(*P1, 1001, 10, "put")                      # reference include/common.h:180
