@@ -32,8 +32,11 @@ typedef enum pcf_status {
   PCF_EODD_N = 2,        /* mc_amer with odd N: reference include/common.h:180 throws                     */
   PCF_ESINGULAR = 3,     /* regression determinant <= 0: reference include/common.h:115-117 throws        */
   PCF_EINVAL = 4,        /* other invalid argument (N <= 0, M <= 0, assets out of range, short replay)    */
-  PCF_ENOTPD = 5,        /* correlation matrix not positive definite (reference include/mvn.h:72-76 falls
-                            back to an eigen-decomposition; this build reports it)                       */
+  PCF_ENOTPD = 5,        /* covariance matrix has a genuinely negative eigenvalue. A positive SEMI-definite
+                            matrix is NOT an error: like the reference (include/mvn.h:68-76) every basket
+                            entry point falls back from Cholesky to eigenvectors * sqrt(eigenvalues); where
+                            the reference's cwiseSqrt then meets a negative eigenvalue it prices NaN -- that
+                            case is reported with this code instead                                       */
   PCF_ECUDA = 10,        /* CUDA runtime failure or no device; pcf_last_error() has the text              */
   PCF_ENCCL = 11,        /* NCCL failure or libnccl.so.2 not loadable                                     */
   PCF_ENOINIT = 12,      /* pcf_init()/pcf_init_rank() not called                                         */
@@ -121,7 +124,10 @@ PCF_API int pcf_world_size(void);
 /* --- the hot path ----------------------------------------------------------------------------- */
 /* replaces mc_eur(),   reference src/mc_eur.cpp:5-27                                             */
 PCF_API int pcf_mc_eur(const pcf_params* p, pcf_result* out);
-/* replaces mc_eur() + mvnorm(), reference src/mc_eur_multi.cpp:6-35, include/mvn.h:42-82        */
+/* replaces mc_eur() + mvnorm(), reference src/mc_eur_multi.cpp:6-35, include/mvn.h:42-82 -- both branches of
+ * mvn.h:68-76: Cholesky factor, or (rho = 1, rho = -1/(d-1): LLT meets a zero pivot) the eigen-decomposition.
+ * Eigenvalues within 1e-10 * lambda_max below zero are rounding noise of a semi-definite matrix and count as 0
+ * (the reference's sqrt of such a value is NaN by accident of rounding). */
 PCF_API int pcf_mc_eur_multi(const pcf_params* p, pcf_result* out);
 /* General basket: the same pricing loop (src/mc_eur_multi.cpp:23-34) with what the reference hard-wires
  * made explicit. Every pointer is a HOST array and may be NULL, which selects the reference's value:

@@ -46,6 +46,7 @@ def lib() -> ctypes.CDLL:
         L.oracle_mc_amer_lsm.argtypes = [_d] * 5 + [_ll, _i, _i, _P, ctypes.POINTER(_i)]
         L.oracle_chol_equicorr.restype = _i
         L.oracle_chol_equicorr.argtypes = [_i, _d, _P]
+        L.oracle_mvn_transform.argtypes = [_i, _d, _P, ctypes.POINTER(_i)]
         L.oracle_mc_basket.restype = _d
         L.oracle_mc_basket.argtypes = [_d] * 5 + [_ll, _i, _i, _d, _P, _P, _P, ctypes.POINTER(_i)]
         L.oracle_mc_basket_general.restype = _d
@@ -123,13 +124,21 @@ def chol_equicorr(d: int, rho: float) -> np.ndarray:
     return L
 
 
+def mvn_transform(d: int, rho: float):
+    """include/mvn.h:53-76: (normTransform row-major d x d, used_eigen). Cholesky factor, or eigenvectors *
+    sqrt(eigenvalues) when LLT reports a non-positive pivot (may hold NaN, exactly as in the reference)."""
+    A = np.zeros((d, d), dtype=np.float64)
+    eig = _i()
+    lib().oracle_mvn_transform(d, rho, _p(A), ctypes.byref(eig))
+    return A, bool(eig.value)
+
+
 def mc_basket(S0, E, r, sigma, T, N, payoff_fun, d, rho, Z, moments=False):
+    """src/mc_eur_multi.cpp:6-35 + include/mvn.h, both branches of mvn.h:68-76 (NaN where the reference gives NaN)."""
     Z = np.ascontiguousarray(Z, dtype=np.float64)
     s, s2, st = _d(), _d(), _i()
     price = lib().oracle_mc_basket(S0, E, r, sigma, T, N, _cp(payoff_fun), d, rho, _p(Z), ctypes.byref(s),
                                    ctypes.byref(s2), ctypes.byref(st))
-    if st.value:
-        raise ValueError("not positive definite")
     return (price, s.value, s2.value) if moments else price
 
 

@@ -10,12 +10,13 @@
 //     against the unmodified reference compiled from /root/reference (oracle/_ref/*_fn, seed pinned
 //     through --wrap=time) -- see tests/golden/reference_vectors.json + tests/golden/make_golden.py
 //     -- and against the reference's own published results/results_binom_embar.csv rows.
-//   * mc_basket (reference src/mc_eur_multi.cpp + include/mvn.h): STREAM-LEVEL PARITY UNPINNED.
-//     The arithmetic lives in Eigen 3 / Boost.Random, which are neither vendored in the reference
-//     nor present in this image and have no pinned version; the reference holds only statistical
-//     results for it (results/results_mc_eur_multi.csv). The restatement follows mvn.h:53-80 and
-//     mc_eur_multi.cpp:23-34 with the replay layout Z[n*d + a] (column-major d x N) and is anchored
-//     analytically (d=1 == mc_eur; rho -> 1 == Black-Scholes; CSV row 11.92 +- MC error).
+//   * mc_basket (reference src/mc_eur_multi.cpp + include/mvn.h): PINNED against the unmodified reference
+//     translation unit compiled with the stand-in Eigen / Boost.Random headers of oracle/shim/ (the image has
+//     neither library and the reference pins no version of them): oracle/_ref/mc_eur_multi_fn. That pins
+//     everything the reference's own code decides -- covariance build, Cholesky-or-eigen branch, draw order
+//     Z[n*d + a], the product normTransform * Z, the missing sqrt(T), weights, payoff, discount.
+//     The factorisations underneath (LLT, SelfAdjointEigenSolver) are the stand-in's, used here through the
+//     same API calls mvn.h makes; Eigen's own kernels could differ from them in the last bits.
 //
 // Every function takes the normal variates as an input array ("replay stream", reference draw
 // order) so that the same stream can be fed to the CUDA kernels.
@@ -26,6 +27,7 @@
 #include <random>
 #include <vector>
 #include <omp.h>
+#include "shim/Eigen/Dense"  // the same stand-in LLT / SelfAdjointEigenSolver the compiled reference links (oracle/shim)
 
 #define ORACLE_API extern "C" __attribute__((visibility("default")))
 
@@ -287,13 +289,42 @@ static double basket_core(double S0, double E, double r, double sigma, double T,
   return (std::exp(-r * T) * acc) / (double)N;
 }
 
+ORACLE_API double oracle_mc_basket_general(const double* S0, double E, double r, const double* sigma, double T,
+                                           long long N, int cp, int d, const double* A, const double* w,
+                                           const double* Z, double* sum_out, double* sumsq_out);
+
+// a4: reference include/mvn.h:53-76 call for call: covar (1 on the diagonal, rho elsewhere), LLT, and when that
+// reports a non-positive pivot the eigen-decomposition fallback eigenvectors * sqrt(eigenvalues) (NaN entries where an
+// eigenvalue of the semi-definite matrix comes out as -1e-17: that is what the reference computes). A is row-major
+// d x d; *used_eigen says which branch was taken.
+ORACLE_API void oracle_mvn_transform(int d, double rho, double* A, int* used_eigen) {
+  Eigen::MatrixXd covar(d, d);
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) covar(i, j) = (i != j) ? rho : 1;
+  Eigen::MatrixXd normTransform(d, d);
+  Eigen::LLT<Eigen::MatrixXd> cholSolver(covar);
+  if (cholSolver.info() == Eigen::Success) {
+    normTransform = cholSolver.matrixL();
+    *used_eigen = 0;
+  } else {
+    Eigen::SelfAdjointEigenSolver<Eigen::MatrixXd> eigenSolver(covar);
+    normTransform = eigenSolver.eigenvectors() * eigenSolver.eigenvalues().cwiseSqrt().asDiagonal();
+    *used_eigen = 1;
+  }
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) A[(size_t)i * d + j] = normTransform(i, j);
+}
+
+// a4 + a5 as the reference runs them: status 0 = Cholesky branch, 1 = eigen branch (never fails: a matrix with a
+// negative eigenvalue yields NaN samples and a NaN price in the reference, and so here).
 ORACLE_API double oracle_mc_basket(double S0, double E, double r, double sigma, double T,
                                    long long N, int cp, int d, double rho, const double* Z,
                                    double* sum_out, double* sumsq_out, int* status) {
-  std::vector<double> L((size_t)d * d);
-  *status = oracle_chol_equicorr(d, rho, L.data());
-  if (*status) return NAN;
-  return basket_core(S0, E, r, sigma, T, N, cp, d, L.data(), Z, sum_out, sumsq_out, false);
+  std::vector<double> A((size_t)d * d);
+  oracle_mvn_transform(d, rho, A.data(), status);
+  if (*status == 0) return basket_core(S0, E, r, sigma, T, N, cp, d, A.data(), Z, sum_out, sumsq_out, false);
+  std::vector<double> S0v((size_t)d, S0), sg((size_t)d, sigma), w((size_t)d, 1.0 / (double)d);
+  return oracle_mc_basket_general(S0v.data(), E, r, sg.data(), T, N, cp, d, A.data(), w.data(), Z, sum_out, sumsq_out);
 }
 
 // the same pricing loop (mc_eur_multi.cpp:23-34) with what the reference hard-wires made explicit:

@@ -11,6 +11,7 @@
 // NCCL is bound lazily through dlopen("libnccl.so.2") so that single-GPU use has no NCCL
 // dependency and a host process that already carries NCCL (PyTorch) shares its copy.
 #include <dlfcn.h>
+#include <algorithm>
 #include <cstdlib>
 #include <chrono>
 #include <cmath>
@@ -515,10 +516,26 @@ int pcf_mc_eur_multi(const pcf_params* p, pcf_result* out) {
   int s = check_common(p, out);
   if (s == PCF_OK && (p->assets < 1 || p->assets > PCF_MAX_ASSETS)) s = PCF_EINVAL;
   if (s == PCF_OK && p->replay && p->replay_len < p->N * (long long)p->assets) s = PCF_EINVAL;
-  double L[PCF_MAX_ASSETS * PCF_MAX_ASSETS];
-  if (s == PCF_OK) s = pcf_chol_equicorr(p->assets, p->rho, L);
   if (s != PCF_OK) { if (out) out->status = s; return s; }
-  return basket_call(p, L, nullptr, out);
+  const int d = p->assets;
+  double L[PCF_MAX_ASSETS * PCF_MAX_ASSETS];
+  s = pcf_chol_equicorr(d, p->rho, L);
+  if (s == PCF_OK) return basket_call(p, L, nullptr, out);
+  // mvn.h:68-76: LLT reported a non-positive pivot -> eigenvectors * sqrt(eigenvalues) of the same matrix. A positive
+  // SEMI-definite matrix (rho = 1, rho = -1/(d-1)) prices through this branch as it does in the reference; a matrix with
+  // a genuinely negative eigenvalue (rho < -1/(d-1), where the reference's cwiseSqrt yields NaN samples) is PCF_ENOTPD.
+  double cov[PCF_MAX_ASSETS * PCF_MAX_ASSETS], S0[PCF_MAX_ASSETS], sg[PCF_MAX_ASSETS], w[PCF_MAX_ASSETS];
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) cov[i * d + j] = (i != j) ? p->rho : 1.0;  // mvn.h:55-60
+  s = pcf_normal_transform(d, cov, L, nullptr);
+  if (s != PCF_OK) { out->status = s; return s; }
+  for (int i = 0; i < d; ++i) {
+    S0[i] = p->S0;
+    sg[i] = p->sigma;
+    w[i] = 1.0 / (double)d;  // mc_eur_multi.cpp:23
+  }
+  BasketHost spec{S0, sg, w, true};
+  return basket_call(p, L, &spec, out);
 }
 
 // Cyclic Jacobi eigen-decomposition of a symmetric d x d matrix (row-major): V's columns are the eigenvectors,
@@ -556,7 +573,17 @@ static void jacobi_eigen(int d, const double* Sin, double* V, double* lam) {
         }
       }
   }
-  for (int i = 0; i < d; ++i) lam[i] = A[i * d + i];
+  // Eigen's documented convention (SelfAdjointEigenSolver): eigenvalues in increasing order, eigenvectors permuted with
+  // them. The order matters: column k of the transform multiplies the k-th normal of a path (mvn.h:74-79).
+  std::vector<int> order(d);
+  for (int i = 0; i < d; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return A[x * d + x] < A[y * d + y]; });
+  std::vector<double> Vs((size_t)d * d);
+  for (int j = 0; j < d; ++j) {
+    lam[j] = A[order[j] * d + order[j]];
+    for (int i = 0; i < d; ++i) Vs[i * d + j] = V[i * d + order[j]];
+  }
+  std::copy(Vs.begin(), Vs.end(), V);
 }
 
 int pcf_normal_transform(int d, const double* cov, double* A, int* used_eigen) {

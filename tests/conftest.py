@@ -16,7 +16,7 @@ def pytest_configure(config):
 def golden():
     import json
     g = {}
-    for name in ("reference_vectors", "exact_binom", "tree_vectors"):
+    for name in ("reference_vectors", "exact_binom", "tree_vectors", "basket_vectors"):
         with open(os.path.join(ROOT, "tests", "golden", name + ".json")) as f:
             g[name] = json.load(f)
     return g

@@ -3,6 +3,9 @@ binaries oracle/Makefile compiles from the unmodified reference sources into ora
 
     make -C oracle all && python tests/golden/make_golden.py
 
+basket_vectors.json     outputs of the unmodified src/mc_eur_multi.cpp + include/mvn.h compiled against the stand-in
+                        Eigen / Boost.Random headers of oracle/shim/ (oracle/_ref/mc_eur_multi_fn), and the published
+                        Serial rows of results/results_mc_eur_multi.csv (statistical pins)
 reference_vectors.json  outputs of the compiled reference (function-level harness, %.17g, RNG seed
                         pinned through --wrap=time) + the published rows of
                         /root/reference/results/results_binom_embar.csv
@@ -148,8 +151,48 @@ def tree_vectors():
     return out
 
 
+def basket_vectors():
+    """mc_eur_multi: d in {1, 4, 16} as the verdict asks, both payoffs, T != 1 (pins the missing sqrt(T),
+    SURVEY F9), a negative rho, and the eigen-decomposition branch of mvn.h:72-76 (rho = 1 at d = 2, where LLT meets a
+    zero pivot and the stand-in solver's eigenvalues are exactly {0, 2}). `used_eigen` records the branch the reference
+    took (restated by oracle.mvn_transform through the same API calls); a NaN price is recorded as null -- that IS the
+    reference's output when an eigenvalue of the semi-definite matrix comes out as -1e-17."""
+    import math
+    assert oracle.have_ref(), "build oracle/_ref first (make -C oracle ref)"
+    out = {"_how": "oracle/_ref/mc_eur_multi_fn <argv>, PCF_FIXED_TIME=<seed>; replay stream = std::mt19937(seed) + "
+                   "std::normal_distribution<>{0,1}, Z[n*d + a]; see oracle/shim/ and tests/golden/make_golden.py",
+           "mc_eur_multi": [], "mc_eur_multi_csv": []}
+    P1 = (100, 100, 0.05, 0.2, 1)
+    P4 = (100, 100, 0.1, 0.2, 1)      # the reference Makefile's mc_eur_multi_tst parameters (Makefile:165-169)
+    PT = (90, 100, 0.03, 0.4, 2.5)    # T != 1
+    for seed, pf, P, N, d, rho in [(42, "call", P1, 100_000, 1, 0.0), (42, "call", P1, 100_000, 4, 0.5),
+                                   (42, "call", P1, 50_000, 16, 0.5), (7, "put", P1, 50_001, 16, 0.5),
+                                   (42, "call", P4, 1_000_000, 4, 0.5), (3, "put", PT, 20_000, 4, 0.3),
+                                   (3, "call", PT, 20_000, 16, 0.9), (5, "call", P1, 30_000, 5, -0.2),
+                                   (9, "call", P1, 40_000, 32, 0.5), (1, "call", P1, 1, 3, 0.5),
+                                   (42, "call", P1, 100_000, 2, 1.0), (11, "put", PT, 20_000, 2, 1.0),
+                                   (42, "call", P1, 10_000, 4, 1.0), (42, "call", P1, 10_000, 3, -0.5)]:
+        price = oracle.ref_fn("mc_eur_multi", pf, *P, N, d, rho, seed=seed)
+        A, eig = oracle.mvn_transform(d, rho)
+        out["mc_eur_multi"].append({"seed": seed, "payoff": pf, "params": P, "N": N, "assets": d, "rho": rho,
+                                    "used_eigen": eig, "price": None if math.isnan(price) else price})
+        print("mc_eur_multi", pf, P, N, d, rho, eig, price, flush=True)
+    for line in open("/root/reference/results/results_mc_eur_multi.csv"):
+        f = line.strip().split(",")
+        if len(f) >= 14 and f[0] == "Serial" and f[1] in ("call", "put"):
+            try:
+                out["mc_eur_multi_csv"].append({"payoff": f[1], "params": [float(x) for x in f[2:7]], "N": int(f[7]),
+                                                "assets": int(f[10]), "price": float(f[13]),
+                                                "source": "results/results_mc_eur_multi.csv"})
+            except ValueError:
+                continue
+    return out
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ref", "exact", "trees"]
+    which = sys.argv[1:] or ["ref", "exact", "trees", "basket"]
+    if "basket" in which:
+        json.dump(basket_vectors(), open(os.path.join(HERE, "basket_vectors.json"), "w"), indent=1)
     if "trees" in which:
         json.dump(tree_vectors(), open(os.path.join(HERE, "tree_vectors.json"), "w"), indent=1)
     if "ref" in which:

@@ -134,6 +134,38 @@ def test_basket_replay_vs_oracle(gpu):
         assert rel(g.price, o) < REPLAY_TOL, (d, rho)
 
 
+def test_basket_replay_vs_compiled_reference(gpu, golden):
+    # tests/golden/basket_vectors.json: the UNMODIFIED src/mc_eur_multi.cpp + include/mvn.h (compiled against oracle/shim)
+    # run on std::mt19937(seed) normals; the GPU consumes the same stream, Z[n*d + a]. Covers both branches of
+    # mvn.h:68-76 through the reference's own entry point (pcf_mc_eur_multi), d = 1..32, T != 1.
+    n_eig = 0
+    for c in golden["basket_vectors"]["mc_eur_multi"]:
+        S0, E, r, sigma, T = c["params"]
+        d, N = c["assets"], c["N"]
+        Z = oracle.normals_mt19937(c["seed"], 1.0, N * d)
+        g = gpu.mc_eur_multi(S0, E, r, sigma, T, N, c["payoff"], d, c["rho"], replay=Z)
+        if c["price"] is not None:
+            assert abs(g.price - c["price"]) <= REPLAY_TOL * max(abs(c["price"]), 1e-3), c
+            n_eig += c["used_eigen"]
+        else:
+            # the reference printed NaN: an eigenvalue of the semi-definite matrix came out as -1e-17 and mvn.h:75 took
+            # its square root. The product counts it as 0 (include/pcf.h) and must agree with the restatement fed the
+            # product's own factor.
+            assert c["used_eigen"] and math.isfinite(g.price)
+            cov = np.full((d, d), c["rho"]); np.fill_diagonal(cov, 1.0)
+            A, eig = gpu.normal_transform(cov)
+            assert eig and np.allclose(A @ A.T, cov, atol=1e-12)
+            o = oracle.mc_basket_general(S0, E, r, sigma, T, N, c["payoff"], A, np.full(d, 1.0 / d), Z)
+            assert rel(g.price, o) < REPLAY_TOL, c
+    assert n_eig >= 2
+    # rho = 1 (every asset driven by the same combination of normals) collapses to one asset: Black-Scholes, native mode
+    g = gpu.mc_eur_multi(*P1, 4_000_000, "call", 8, 1.0, seed=12)
+    assert abs(g.price - BS_CALL) < 3 * g.std_error
+    # rho = -1/(d-1): the basket's driving noise sums to zero variance in the equal-weight direction; finite, below BS
+    g = gpu.mc_eur_multi(*P1, 1_000_000, "call", 3, -0.5, seed=12)
+    assert math.isfinite(g.price) and 0 < g.price < BS_CALL
+
+
 def test_basket_equicorrelation_fast_path_is_bit_identical(gpu, monkeypatch):
     # the constant-column shortcut performs the same chain of FMAs as the general triangular product
     for d, rho, N in [(16, 0.5, 300_001), (5, -0.1, 100_000), (32, 0.3, 50_000), (1, 0.0, 10_000), (2, 0.9, 10_001)]:

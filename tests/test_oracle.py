@@ -120,8 +120,40 @@ def test_binom_converges_to_black_scholes():
     assert abs(oracle.binom(100, 100, .05, .2, 1, 4000, "put") - BS_PUT) < 2e-3
 
 
+def test_mc_basket_matches_reference(golden):
+    # The unmodified src/mc_eur_multi.cpp + include/mvn.h compiled against the stand-in Eigen/Boost headers (oracle/shim):
+    # both branches of mvn.h:68-76, d = 1..32, T != 1, both payoffs; a null price is the reference's NaN.
+    n_eig = 0
+    for c in golden["basket_vectors"]["mc_eur_multi"]:
+        S0, E, r, sigma, T = c["params"]
+        d = c["assets"]
+        Z = oracle.normals_mt19937(c["seed"], 1.0, c["N"] * d)
+        got = oracle.mc_basket(S0, E, r, sigma, T, c["N"], c["payoff"], d, c["rho"], Z)
+        assert oracle.mvn_transform(d, c["rho"])[1] == c["used_eigen"], c
+        n_eig += c["used_eigen"]
+        if c["price"] is None:
+            assert math.isnan(got), c
+        else:
+            assert got == c["price"] or rel(got, c["price"]) < 1e-15, c
+    assert n_eig >= 3
+
+
+def test_mc_basket_published_rows_are_statistically_consistent(golden):
+    # results/results_mc_eur_multi.csv (Serial rows, d = 4): each published price lies within 5 standard errors of the
+    # restatement on an independent stream of the same N (the reference's seed was time(), so nothing tighter exists)
+    rows = [c for c in golden["basket_vectors"]["mc_eur_multi_csv"] if c["N"] <= 1_000_000 and c["assets"] == 4]
+    assert len(rows) >= 3
+    for c in rows[:6]:
+        S0, E, r, sigma, T = c["params"]
+        N = c["N"]
+        Z = oracle.normals_mt19937(1234 + N, 1.0, N * 4)
+        v, s, s2 = oracle.mc_basket(S0, E, r, sigma, T, N, c["payoff"], 4, 0.5, Z, moments=True)   # runscript: rho=0.5
+        se = math.exp(-r * T) * math.sqrt(max(s2 / N - (s / N) ** 2, 0) / N)
+        assert abs(v - c["price"]) < 5 * math.sqrt(2) * se + 1e-9, (c, v, se)
+
+
 def test_basket_anchors():
-    # stream-level parity for the basket is unpinned (Eigen/Boost absent); analytic anchors instead
+    # analytic anchors next to the compiled-reference vectors above
     N = 200000
     w = oracle.normals_mt19937(5, 1.0, N)
     # d = 1: identical to mc_eur at T = 1
@@ -139,6 +171,11 @@ def test_basket_anchors():
     assert np.allclose(np.diag(C), 1.0, atol=1e-14) and np.allclose(C - np.diag(np.diag(C)), 0.5 * (1 - np.eye(16)), atol=1e-14)
     with pytest.raises(ValueError):
         oracle.chol_equicorr(4, -0.5)  # not positive definite (rho < -1/(d-1))
+    # mvn.h:68-76: LLT fails on the singular matrix -> eigen branch; A A^T still reproduces the matrix
+    A, eig = oracle.mvn_transform(2, 1.0)
+    assert eig and np.allclose(A @ A.T, np.ones((2, 2)), atol=1e-14)
+    A, eig = oracle.mvn_transform(16, 0.5)
+    assert not eig and np.array_equal(A, L)
 
 
 def test_general_basket_reduces_to_reference_basket():
@@ -212,6 +249,12 @@ def test_restatement_equals_compiled_reference_on_random_parameters():
                 oracle.mc_amer(S0, E, r, sigma, T, N, M, pf, w)
         else:
             assert oracle.mc_amer(S0, E, r, sigma, T, N, M, pf, w) == want
+        d = int(rng.integers(1, 20))
+        rho = float(rng.uniform(-1.0 / max(d - 1, 1) + 1e-3, 1.0)) if k % 5 else 1.0   # every 5th: the eigen branch
+        Z = oracle.normals_mt19937(seed, 1.0, N * d)
+        got, want = oracle.mc_basket(S0, E, r, sigma, T, N, pf, d, rho, Z), \
+            oracle.ref_fn("mc_eur_multi", pf, S0, E, r, sigma, T, N, d, rho, seed=seed)
+        assert got == want or (math.isnan(got) and math.isnan(want)), (k, d, rho, got, want)
         Nt = int(rng.integers(1, 400))
         assert oracle.binom_tree(S0, E, r, sigma, T, Nt, pf, False) == \
             oracle.ref_fn("binom_vanilla_eur", pf, S0, E, r, sigma, T, Nt)
