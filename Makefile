@@ -2,9 +2,13 @@
 NVCC      ?= /usr/local/cuda/bin/nvcc
 HOSTCXX   := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off
+# TUNING=1 adds the launch-shape A/B instantiations and their PCF_* environment knobs (tools/tune_*.py); the shipped
+# library has one instantiation per kernel family and reads no environment variable on a pricing call.
+TUNEFLAG  := $(if $(TUNING),-DPCF_TUNING,)
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off --compress-mode=size $(TUNEFLAG)
+LOGDIR    := build/ptxas
 CSRC      := parcompfin_b200/csrc
-SRCS      := $(CSRC)/pcf_api.cu $(CSRC)/mc_kernels.cu $(CSRC)/amer_kernels.cu $(CSRC)/binom_kernels.cu $(CSRC)/tree_kernels.cu $(CSRC)/peaks.cu
+SRCS      := $(CSRC)/pcf_api.cu $(CSRC)/mc_kernels.cu $(CSRC)/basket_kernels.cu $(CSRC)/amer_kernels.cu $(CSRC)/binom_kernels.cu $(CSRC)/tree_kernels.cu $(CSRC)/peaks.cu
 OBJS      := $(SRCS:.cu=.o) $(CSRC)/fastmath_tables.o
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/pcf.h
 LIB       := parcompfin_b200/libpcf.so
@@ -16,7 +20,8 @@ all: lib bins oracle
 
 lib: $(LIB)
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
-	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(@:.o=.ptxas.log) || { cat $(@:.o=.ptxas.log); exit 1; }
+	@mkdir -p $(LOGDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(LOGDIR)/$(notdir $(@:.o=.log)) || { cat $(LOGDIR)/$(notdir $(@:.o=.log)); exit 1; }
 $(CSRC)/fastmath_tables.o: $(CSRC)/fastmath_tables.cpp $(CSRC)/fastmath.cuh
 	$(HOSTCXX) -std=c++17 -O2 -fPIC -fvisibility=hidden -ffp-contract=off -c $< -o $@
 $(LIB): $(OBJS)
@@ -31,7 +36,7 @@ oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -f $(OBJS) $(CSRC)/*.ptxas.log $(LIB) $(BINS)
+	rm -rf $(OBJS) $(LOGDIR) $(LIB) $(BINS)
 
 # ---- the reference's own target names (reference Makefile:14-16,34,68,100,131,159), so that its run-scripts and habits
 # keep working: `make init`, `make mc_eur_bin` (called by runscript_mc_eur.sh:25 after it rewrites include/comparison.h),

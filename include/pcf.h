@@ -58,6 +58,14 @@ typedef enum pcf_status {
                                       underflow rule's threshold with margin; the sum is bit-identical either way
                                       (tests assert it), the flag exists so both rates can be reported.            */
 
+#define PCF_FLAG_BASKET_GENERAL 0x8u /* mc_eur_multi: price the reference's equicorrelation basket with the general
+                                      triangular-product kernel instead of the constant-column fast path (same chain of
+                                      FMAs, bit-identical sums; tests assert it)                                       */
+
+#define PCF_FLAG_TREE_WARP 0x10u   /* binom_vanilla_*: warp-trapezoid tiling (every warp independent) instead of the
+                                      CTA-cooperative one picked per launch; same per-node operations, bit-identical
+                                      root (tests assert it). Lattices with p or q outside [0,1] always take it.       */
+
 /* Normal-stream ids (word 3 of the Philox counter), one per method. */
 #define PCF_STREAM_EUR 0u
 #define PCF_STREAM_ASIA 1u

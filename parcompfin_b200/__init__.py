@@ -24,6 +24,8 @@ PCF_ECUDA, PCF_ENCCL, PCF_ENOINIT, PCF_ENOMEM = 10, 11, 12, 13
 PCF_FLAG_BINOM_WINDOW = 0x1
 PCF_FLAG_AMER_LSM = 0x2
 PCF_FLAG_BINOM_NOSCREEN = 0x4
+PCF_FLAG_BASKET_GENERAL = 0x8
+PCF_FLAG_TREE_WARP = 0x10
 STREAM_EUR, STREAM_ASIA, STREAM_BASKET, STREAM_AMER = 0, 1, 2, 3
 MAX_ASSETS = 32
 
@@ -237,10 +239,11 @@ def mc_eur(S0, E, r, sigma, T, N, payoff_fun, *, seed=0, replay=None) -> Result:
     return _call("pcf_mc_eur", S0, E, r, sigma, T, N, payoff_fun, seed=seed, replay=replay)
 
 
-def mc_eur_multi(S0, E, r, sigma, T, N, payoff_fun, assets, rho, *, seed=0, replay=None) -> Result:
-    """reference src/mc_eur_multi.cpp:6-35 (the function is also called mc_eur there)"""
+def mc_eur_multi(S0, E, r, sigma, T, N, payoff_fun, assets, rho, *, seed=0, replay=None, general=False) -> Result:
+    """reference src/mc_eur_multi.cpp:6-35 (the function is also called mc_eur there). ``general=True``
+    (PCF_FLAG_BASKET_GENERAL) prices through the general triangular kernel instead of the equicorrelation fast path."""
     return _call("pcf_mc_eur_multi", S0, E, r, sigma, T, N, payoff_fun, assets=assets, rho=rho,
-                 seed=seed, replay=replay)
+                 seed=seed, replay=replay, flags=PCF_FLAG_BASKET_GENERAL if general else 0)
 
 
 def mc_basket(S0, E, r, sigma, T, N, payoff_fun, assets, *, rho=0.0, weights=None, cov=None, transform=None,
@@ -301,14 +304,17 @@ def binom(S0, E, r, sigma, T, N, payoff_fun, *, window=False, screen=True) -> Re
                  flags=(PCF_FLAG_BINOM_WINDOW if window else 0) | (0 if screen else PCF_FLAG_BINOM_NOSCREEN))
 
 
-def binom_vanilla_eur(S0, E, r, sigma, T, N, payoff_fun) -> Result:
-    """reference src/binom_vanilla_eur.cpp:5-41 (backward-induction tree; `units` = node updates)"""
-    return _call("pcf_binom_vanilla_eur", S0, E, r, sigma, T, N, payoff_fun)
+def binom_vanilla_eur(S0, E, r, sigma, T, N, payoff_fun, *, warp_tiling=False) -> Result:
+    """reference src/binom_vanilla_eur.cpp:5-41 (backward-induction tree; `units` = node updates).
+    ``warp_tiling=True`` (PCF_FLAG_TREE_WARP): the warp-trapezoid kernel instead of the CTA-cooperative one."""
+    return _call("pcf_binom_vanilla_eur", S0, E, r, sigma, T, N, payoff_fun,
+                 flags=PCF_FLAG_TREE_WARP if warp_tiling else 0)
 
 
-def binom_vanilla_amer(S0, E, r, sigma, T, N, payoff_fun) -> Result:
+def binom_vanilla_amer(S0, E, r, sigma, T, N, payoff_fun, *, warp_tiling=False) -> Result:
     """reference src/binom_vanilla_amer.cpp:5-42 (American tree; `units` = node updates)"""
-    return _call("pcf_binom_vanilla_amer", S0, E, r, sigma, T, N, payoff_fun)
+    return _call("pcf_binom_vanilla_amer", S0, E, r, sigma, T, N, payoff_fun,
+                 flags=PCF_FLAG_TREE_WARP if warp_tiling else 0)
 
 
 # ---- diagnostics ---------------------------------------------------------------------------------

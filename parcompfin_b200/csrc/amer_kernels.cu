@@ -268,7 +268,6 @@ struct SweepArgs {
   int first;            // date M: no decision
   int lsm;              // PCF_FLAG_AMER_LSM
   int stages;
-  int dbg;              // PCF_AMER_DBG: experiments
   const double* mom_in;
   double* partials;
   unsigned int* ticket;
@@ -359,7 +358,6 @@ __global__ void __launch_bounds__(kSweepBlock, kCtas) amer_sweep_kernel(SweepArg
       uint64_t pol, pol_keep;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
       asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
-      if (a.dbg & 32) pol_keep = pol;
       int s = 0;
       uint32_t ph = 0;
       for (long long tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
@@ -610,12 +608,17 @@ static int launch_sweep2(Ctx& c, bool final_date, int grid, int stages, const Sw
 template <typename WT>
 static int launch_sweep(Ctx& c, bool final_date, int grid, int stages, int per_sm, bool early, const SweepArgs& a,
                         const PeerLink& li, const PeerLink& lo) {
+#ifdef PCF_TUNING
   if (per_sm >= 3) {
     return early ? launch_sweep2<WT, true, 3>(c, final_date, grid, stages, a, li, lo)
                  : launch_sweep2<WT, false, 3>(c, final_date, grid, stages, a, li, lo);
   }
   return early ? launch_sweep2<WT, true, 2>(c, final_date, grid, stages, a, li, lo)
                : launch_sweep2<WT, false, 2>(c, final_date, grid, stages, a, li, lo);
+#else
+  (void)per_sm; (void)early;
+  return launch_sweep2<WT, false, kSweepCtasPerSM>(c, final_date, grid, stages, a, li, lo);
+#endif
 }
 
 static inline size_t amer_when_bytes(int M) { return M <= WhenBits<uint8_t>::kMask ? 1 : 2; }
@@ -666,8 +669,8 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
     int grid_gen = grid_for(c, H, kAmerBlock, 2);
     amer_paths_kernel<true, 1, 2><<<grid_gen, kAmerBlock, gen_smem, c.stream>>>(a, c.d_tables, paths);
   } else {
-    // launch shape: PCF_AMER_GEN = <pairs per thread><CTAs per SM> (tuning knob)
-    const char* v = getenv("PCF_AMER_GEN");
+    // launch shape: PCF_AMER_GEN = <pairs per thread><CTAs per SM> (PCF_TUNING builds)
+    const char* v = tuning_env("PCF_AMER_GEN");
     const int variant = v ? atoi(v) : 32;  // ncu, 1e8 x 50: 32 -> 9.1 ms, 22 -> 9.6, 23 -> 9.9, 14 -> 10.5
 #define PCF_GEN_CASE(P, B)                                                                       \
   case P * 10 + B: {                                                                             \
@@ -675,13 +678,15 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
     amer_paths_kernel<false, P, B><<<grid_gen, kAmerBlock, gen_smem, c.stream>>>(a, c.d_tables, paths); \
   } break;
     switch (variant) {
+#ifdef PCF_TUNING
       PCF_GEN_CASE(1, 4)
       PCF_GEN_CASE(2, 2)
       PCF_GEN_CASE(2, 3)
-      PCF_GEN_CASE(3, 2)
       PCF_GEN_CASE(4, 1)
       PCF_GEN_CASE(4, 2)
       PCF_GEN_CASE(6, 1)
+#endif
+      PCF_GEN_CASE(3, 2)
       default:
         set_last_error("unknown PCF_AMER_GEN");
         return PCF_EINVAL;
@@ -698,9 +703,9 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   // Backward sweep m = M .. 1 (mc_amer.cpp:23-27, 31, 109-111). Kernel for date m consumes the moments of date m
   // and produces those of date m-1. Peer path: moments travel through the NVLink mailboxes (publish in the
   // producing kernel, gather in the consuming one); NCCL path: an all-reduce of the 8 doubles between two kernels.
-  // Launch shape: PCF_AMER_SWEEP = "<ring stages>,<CTAs per SM>,<early gathers 0|1>" (tuning knob).
+  // Launch shape: PCF_AMER_SWEEP = "<ring stages>,<CTAs per SM>,<early gathers 0|1>" (PCF_TUNING builds).
   int stages = 2, per_sm = kSweepCtasPerSM, early = 0;
-  if (const char* v = getenv("PCF_AMER_SWEEP")) {
+  if (const char* v = tuning_env("PCF_AMER_SWEEP")) {
     if (sscanf(v, "%d,%d,%d", &stages, &per_sm, &early) != 3 || stages < 2 || stages > kMaxStages || per_sm < 1 || per_sm > kSweepCtasPerSM) {
       set_last_error("bad PCF_AMER_SWEEP");
       return PCF_EINVAL;
@@ -719,7 +724,6 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   sa.paths = paths; sa.when = when; sa.Np = Np; sa.E = p.E; sa.cp = p.cp; sa.M = M;
   sa.lsm = (p.flags & PCF_FLAG_AMER_LSM) ? 1 : 0;
   sa.stages = stages;
-  sa.dbg = getenv("PCF_AMER_DBG") ? atoi(getenv("PCF_AMER_DBG")) : 0;
   sa.partials = c.d_partials; sa.ticket = c.d_ticket; sa.err_flag = c.d_flag;
   double* mom[2] = {c.d_out + 8, c.d_out + 16};
   PeerLink none = c.link;
@@ -728,7 +732,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   for (int m = M; m >= 1; --m) {
     sa.m = m;
     sa.first = (m == M);
-    sa.rev = (sa.dbg & 32) ? 0 : ((M - m) & 1);
+    sa.rev = (M - m) & 1;
     sa.mom_in = mom[m & 1];
     if (m < M && !use_peer(c)) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));
     const PeerLink l_out = next_link(c);

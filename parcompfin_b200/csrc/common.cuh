@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include "../../include/pcf.h"
 #include "fastmath.cuh"
@@ -11,6 +12,14 @@
 namespace pcf {
 
 void set_last_error(const std::string& s);
+
+// Launch-shape A/B knobs exist only in a -DPCF_TUNING build (`make lib TUNING=1`, used by tools/tune_*.py). The shipped
+// library has one instantiation per kernel family and reads no environment variable on a pricing call.
+#ifdef PCF_TUNING
+inline const char* tuning_env(const char* name) { return getenv(name); }
+#else
+inline const char* tuning_env(const char*) { return nullptr; }
+#endif
 
 #define PCF_CUDA(expr)                                                                        \
   do {                                                                                        \

@@ -12,7 +12,7 @@ constexpr int kInner = 512;
 
 // The addend is a constant-bank operand (the form every Horner step of the production kernels uses): DFMA
 // then issues at its true rate of one warp instruction per 2 cycles per SM sub-partition; with three
-// register operands the register file limits it to ~2.2-2.5 cycles (tests/ubench, profiles/r1_ubench_pipes.log).
+// register operands the register file limits it to ~2.2-2.5 cycles (tools/ubench, profiles/r1_ubench_pipes.log).
 __constant__ double c_peak_addend[8] = {1e-9, 2e-9, 3e-9, 4e-9, 5e-9, 6e-9, 7e-9, 8e-9};
 
 __global__ void __launch_bounds__(kPeakBlock) dfma_chain_kernel(double a, double b, int outer, double* sink) {

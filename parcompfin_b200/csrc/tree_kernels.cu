@@ -300,7 +300,7 @@ static int tree_launch_all(Ctx& c, TreeArgs a, long long N, bool amer, double* b
   // layers (mode 2) hides the launch gap -- 11.1 -> 8.0 ms (European) / 20.0 -> 16.8 ms (American) at N = 1e5, 85 -> 62 ms
   // at N = 4e5. Releasing it at kernel start (mode 1) parks the CTAs of the next launches on the SMs while this one
   // computes and skews their placement: 2x SLOWER for N >= 1e5. PCF_TREE_PDL = 0 | 1 | 2 overrides.
-  const char* pe = getenv("PCF_TREE_PDL");
+  const char* pe = tuning_env("PCF_TREE_PDL");
   const int trig = pe ? atoi(pe) : 2;
   const bool pdl = trig != 0;
   a.trig = trig;
@@ -340,28 +340,42 @@ struct CtaCandidate {
   void (*eur)(TreeArgs);
   void (*amer)(TreeArgs);
 };
-#define PCF_CTA_SHAPE_K(R, W, K) \
-  { R, W, K, CtaShape<R, W, K>::kK, CtaShape<R, W, K>::kStride, tree_cta_kernel<R, W, K, false>, tree_cta_kernel<R, W, K, true> }
-#define PCF_CTA_SHAPE(R, W) PCF_CTA_SHAPE_K(R, W, 0)
+#define PCF_CTA_ROW(R, W, K, EUR, AMER) \
+  { R, W, K, CtaShape<R, W, K>::kK, CtaShape<R, W, K>::kStride, EUR, AMER }
+#define PCF_CTA_BOTH(R, W, K) PCF_CTA_ROW(R, W, K, (tree_cta_kernel<R, W, K, false>), (tree_cta_kernel<R, W, K, true>))
+#ifdef PCF_TUNING
+#define PCF_CTA_EUR(R, W, K) PCF_CTA_BOTH(R, W, K)
+#define PCF_CTA_AMER(R, W, K) PCF_CTA_BOTH(R, W, K)
+#else
+#define PCF_CTA_EUR(R, W, K) PCF_CTA_ROW(R, W, K, (tree_cta_kernel<R, W, K, false>), nullptr)
+#define PCF_CTA_AMER(R, W, K) PCF_CTA_ROW(R, W, K, nullptr, (tree_cta_kernel<R, W, K, true>))
+#endif
+#define PCF_CTA_SHAPE(R, W) PCF_CTA_BOTH(R, W, 0)
 static const CtaCandidate kCtaShapes[] = {
-    PCF_CTA_SHAPE(2, 4),  PCF_CTA_SHAPE(3, 4),  PCF_CTA_SHAPE(4, 4),  PCF_CTA_SHAPE(6, 4),  PCF_CTA_SHAPE(8, 4),
-    PCF_CTA_SHAPE(1, 8),  PCF_CTA_SHAPE(2, 8),  PCF_CTA_SHAPE(3, 8),  PCF_CTA_SHAPE(4, 8),  PCF_CTA_SHAPE(6, 8),
-    PCF_CTA_SHAPE(8, 8),  PCF_CTA_SHAPE(2, 12), PCF_CTA_SHAPE(3, 12), PCF_CTA_SHAPE(4, 12), PCF_CTA_SHAPE(6, 12),
-    PCF_CTA_SHAPE(8, 12), PCF_CTA_SHAPE(1, 16), PCF_CTA_SHAPE(2, 16), PCF_CTA_SHAPE(3, 16), PCF_CTA_SHAPE(4, 16),
-    PCF_CTA_SHAPE(6, 16), PCF_CTA_SHAPE(8, 16), PCF_CTA_SHAPE(1, 20), PCF_CTA_SHAPE(8, 20),
-    // 256 layers per launch: half the launches where the layer is narrow enough to afford the wider decaying edge
-    // (measured: 105 instead of 115 cycles per layer below 30 k nodes; wider shapes gain nothing from it)
-    PCF_CTA_SHAPE_K(4, 4, 256), PCF_CTA_SHAPE_K(3, 8, 256), PCF_CTA_SHAPE_K(2, 8, 256), PCF_CTA_SHAPE_K(2, 12, 256),
+    // the shapes the measured per-width tables below select (kRulesEur / kRulesAmer), in the flavour that selects them
+    PCF_CTA_EUR(4, 4, 256), PCF_CTA_EUR(4, 4, 0), PCF_CTA_BOTH(3, 8, 256), PCF_CTA_BOTH(3, 8, 0), PCF_CTA_BOTH(4, 8, 0),
+    PCF_CTA_AMER(2, 8, 256), PCF_CTA_AMER(2, 8, 0), PCF_CTA_AMER(2, 12, 0), PCF_CTA_AMER(6, 4, 0), PCF_CTA_AMER(2, 16, 0),
+    PCF_CTA_AMER(6, 8, 0),
+#ifdef PCF_TUNING
+    // every shape tools/tune_tree4.py measured (profiles/r1s_tune_tree_shapes.log)
+    PCF_CTA_SHAPE(2, 4),  PCF_CTA_SHAPE(3, 4),  PCF_CTA_SHAPE(8, 4),  PCF_CTA_SHAPE(1, 8),  PCF_CTA_SHAPE(8, 8),
+    PCF_CTA_SHAPE(3, 12), PCF_CTA_SHAPE(4, 12), PCF_CTA_SHAPE(6, 12), PCF_CTA_SHAPE(8, 12), PCF_CTA_SHAPE(1, 16),
+    PCF_CTA_SHAPE(3, 16), PCF_CTA_SHAPE(4, 16), PCF_CTA_SHAPE(6, 16), PCF_CTA_SHAPE(8, 16), PCF_CTA_SHAPE(1, 20),
+    PCF_CTA_SHAPE(8, 20), PCF_CTA_BOTH(2, 12, 256),
+#endif
 };
 #undef PCF_CTA_SHAPE
-#undef PCF_CTA_SHAPE_K
+#undef PCF_CTA_BOTH
+#undef PCF_CTA_EUR
+#undef PCF_CTA_AMER
+#undef PCF_CTA_ROW
 
-// Shape of the launch that starts at an n0-node layer. The table is MEASURED (tests/tune_tree4.py: T(N) of every pinned
+// Shape of the launch that starts at an n0-node layer. The table is MEASURED (tools/tune_tree4.py: T(N) of every pinned
 // shape on a grid of N; the slope between two grid points is the cost of one layer at that width; the cheapest shape
 // per interval is listed, profiles/r1s_tune_tree_shapes.log) on a 148-SM B200 and scaled by the SM count. What it
 // encodes: (1) ptxas interleaves the independent node chains of a lane for kR <= 4 but serialises them for kR >= 6
 // (one scratch register pair per node), so more than four nodes per lane only pay when the layer is many waves wide;
-// (2) the FP64 pipe interleaves the chains of ONE warp better than those of several warps (tests/ubench: 8 warps x 1
+// (2) the FP64 pipe interleaves the chains of ONE warp better than those of several warps (tools/ubench: 8 warps x 1
 // chain 3.0 cycles per instruction, 1 warp x 4 chains 2.2), so the European tree prefers one kR = 4 warp per
 // sub-partition; (3) the American node carries three more values per node (S0 u^i, the d-power window, the exercise
 // value) and prefers kR = 2 with 8-16 warps until the layer is wider than one wave; (4) 256 layers per launch pay
@@ -374,23 +388,23 @@ static const ShapeRule kRulesAmer[] = {{30000, 2, 8, 256}, {50000, 2, 8, 0}, {60
                                        {90000, 6, 4, 0}, {100000, 2, 16, 0}, {125000, 4, 8, 0}, {150000, 3, 8, 0},
                                        {200000, 6, 4, 0}, {250000, 4, 8, 0}, {700000, 6, 4, 0}, {-1, 6, 8, 0}};
 
-static const CtaCandidate* tree_find_shape(int kR, int kW, int kKsel) {
+static const CtaCandidate* tree_find_shape(int kR, int kW, int kKsel, bool amer) {
   for (const CtaCandidate& s : kCtaShapes)
-    if (s.kR == kR && s.kW == kW && s.kKsel == kKsel) return &s;
+    if (s.kR == kR && s.kW == kW && s.kKsel == kKsel && (amer ? s.amer : s.eur) != nullptr) return &s;
   return nullptr;
 }
 
 static const CtaCandidate* tree_pick_shape(long long n0, int sms, bool amer, int fixed_r, int fixed_w, int fixed_k) {
-  if (fixed_r) return tree_find_shape(fixed_r, fixed_w, fixed_k);
+  if (fixed_r) return tree_find_shape(fixed_r, fixed_w, fixed_k, amer);
   const double scaled = (double)n0 * 148.0 / (double)std::max(sms, 1);
   for (const ShapeRule* r = amer ? kRulesAmer : kRulesEur;; ++r)
-    if (r->n_max < 0 || scaled <= (double)r->n_max) return tree_find_shape(r->kR, r->kW, r->kKsel);
+    if (r->n_max < 0 || scaled <= (double)r->n_max) return tree_find_shape(r->kR, r->kW, r->kKsel, amer);
 }
 
 // fixed_r/fixed_w != 0 pin one shape for the whole tree (PCF_TREE=1<R><WW>[<K/64>], tests and tuning)
 static int tree_launch_cta(Ctx& c, TreeArgs a, long long N, bool amer, double* buf0, double* buf1, int fixed_r, int fixed_w,
                            int fixed_k) {
-  const char* pe = getenv("PCF_TREE_PDL");
+  const char* pe = tuning_env("PCF_TREE_PDL");
   const int trig = pe ? atoi(pe) : 2;
   a.trig = trig;
   long long n = N;
@@ -473,16 +487,17 @@ int run_binom_tree(Ctx& c, const pcf_params& p, bool american) {
   a.S0 = p.S0; a.sgn = (double)p.cp; a.nE = -a.sgn * p.E;
   tree_terminal_kernel<<<grid_for(c, N + 1, 256, 8), 256, 0, c.stream>>>(buf0, d_pu, d_pd, N, p.S0, a.sgn, a.nE);
   c.launches++;
-  // launch shape (tuning knob): unset = CTA-cooperative kernel, shape chosen per launch; PCF_TREE=1<nodes per lane>
+  // launch shape (PCF_TUNING builds): unset = CTA-cooperative kernel, shape chosen per launch; PCF_TREE=1<nodes per lane>
   // <warps per CTA, two digits>[<layers per launch / 64>] pins one CTA shape (e.g. 1216, 14044); PCF_TREE=<nodes per lane><layers per launch / 8> selects the warp-trapezoid
   // kernel of the first build
-  const char* e = getenv("PCF_TREE");
+  const char* e = tuning_env("PCF_TREE");
   // tree_cta_kernel's American node relies on continuation values >= 0, i.e. on p, q >= 0; a lattice whose rounded
   // probabilities leave [0, 1] (p is within an ulp of 0 or 1 when sigma -> 0) runs the warp kernel, which keeps both maxima
   const bool cta_ok = !american || (pp >= 0.0 && q >= 0.0);
-  if (!e && cta_ok) return tree_launch_cta(c, a, N, american, buf0, buf1, 0, 0, 0);
+  if (!e && cta_ok && !(p.flags & PCF_FLAG_TREE_WARP)) return tree_launch_cta(c, a, N, american, buf0, buf1, 0, 0, 0);
   if (!e) return N > 250000 ? tree_launch_all<4, 32>(c, a, N, american, buf0, buf1)
                             : tree_launch_all<4, 64>(c, a, N, american, buf0, buf1);
+#ifdef PCF_TUNING
   const int shape = atoi(e);
   if (shape >= 1000 && shape < 20000 && !cta_ok) {
     set_last_error("PCF_TREE: the CTA kernel needs p, q >= 0 for the American tree");
@@ -502,6 +517,9 @@ int run_binom_tree(Ctx& c, const pcf_params& p, bool american) {
       set_last_error("unknown PCF_TREE");
       return PCF_EINVAL;
   }
+#else
+  return PCF_EINVAL;  // unreachable: tuning_env() is null in this build
+#endif
 }
 
 }  // namespace pcf

@@ -166,14 +166,12 @@ def test_basket_replay_vs_compiled_reference(gpu, golden):
     assert math.isfinite(g.price) and 0 < g.price < BS_CALL
 
 
-def test_basket_equicorrelation_fast_path_is_bit_identical(gpu, monkeypatch):
+def test_basket_equicorrelation_fast_path_is_bit_identical(gpu):
     # the constant-column shortcut performs the same chain of FMAs as the general triangular product
+    # (PCF_FLAG_BASKET_GENERAL sends the reference's basket through the general kernel)
     for d, rho, N in [(16, 0.5, 300_001), (5, -0.1, 100_000), (32, 0.3, 50_000), (1, 0.0, 10_000), (2, 0.9, 10_001)]:
-        monkeypatch.delenv("PCF_BASKET_GENERAL", raising=False)
         fast = gpu.mc_eur_multi(*P1, N, "call", d, rho, seed=77)
-        monkeypatch.setenv("PCF_BASKET_GENERAL", "1")
-        gen = gpu.mc_eur_multi(*P1, N, "call", d, rho, seed=77)
-        monkeypatch.delenv("PCF_BASKET_GENERAL", raising=False)
+        gen = gpu.mc_eur_multi(*P1, N, "call", d, rho, seed=77, general=True)
         assert rel(fast.sum, gen.sum) < 1e-14 and rel(fast.sumsq, gen.sumsq) < 1e-14, (d, rho)
 
 
@@ -362,24 +360,17 @@ def test_trees_match_published_csv(gpu, golden):
         assert f"{g.price:.10g}" == f"{c['price']:.10g}", c
 
 
-def test_trees_launch_shape_independence_and_properties(gpu, monkeypatch):
-    # the tiling (nodes per lane x layers per launch) must not change a single bit: same operations per node
+def test_trees_launch_shape_independence_and_properties(gpu):
+    # the tiling must not change a single bit (same operations per node): the CTA-cooperative kernel with the shape picked
+    # per launch (default) against the warp-trapezoid kernel (PCF_FLAG_TREE_WARP). A `make lib TUNING=1` build pins
+    # every other shape through PCF_TREE (tools/tune_tree4.py asserts the same equality over all of them).
     P = (100, 100, .05, .2, 1)
-    ref = {}
-    # None: CTA-cooperative kernel, shape picked per launch (the default); 1<R><WW>: one pinned CTA shape (nodes per
-    # lane, warps per CTA); 2-digit shapes: the warp-trapezoid kernel
-    for shape in (None, "44", "22", "48", "88", "84", "1108", "1120", "1204", "1208", "1216", "1304", "1312",
-                  "1404", "1416", "1604", "1612", "1804", "1812", "1820", "14044", "12084", "13084", "12124"):
-        if shape is None:
-            monkeypatch.delenv("PCF_TREE", raising=False)
-        else:
-            monkeypatch.setenv("PCF_TREE", shape)
-        for N in (1, 5, 31, 97, 1000, 5003, 20011):
-            for pf in ("call", "put"):
-                e = gpu.binom_vanilla_eur(*P, N, pf).price
-                a = gpu.binom_vanilla_amer(*P, N, pf).price
-                assert ref.setdefault((N, pf), (e, a)) == (e, a), (shape, N, pf)
-    monkeypatch.delenv("PCF_TREE", raising=False)
+    for N in (1, 5, 31, 97, 1000, 5003, 20011, 70001):
+        for pf in ("call", "put"):
+            e = gpu.binom_vanilla_eur(*P, N, pf).price
+            a = gpu.binom_vanilla_amer(*P, N, pf).price
+            assert (e, a) == (gpu.binom_vanilla_eur(*P, N, pf, warp_tiling=True).price,
+                              gpu.binom_vanilla_amer(*P, N, pf, warp_tiling=True).price), (N, pf)
     # small trees against the oracle, including N not a multiple of anything
     for N in (1, 2, 3, 17, 200, 777):
         for pf in ("call", "put"):
@@ -396,9 +387,8 @@ def test_trees_launch_shape_independence_and_properties(gpu, monkeypatch):
     # wide trees walk every rule of the per-launch shape table (csrc/tree_kernels.cu: tree_pick_shape)
     N = 600_000
     auto = (gpu.binom_vanilla_eur(*P, N, "put").price, gpu.binom_vanilla_amer(*P, N, "put").price)
-    monkeypatch.setenv("PCF_TREE", "44")
-    assert auto == (gpu.binom_vanilla_eur(*P, N, "put").price, gpu.binom_vanilla_amer(*P, N, "put").price)
-    monkeypatch.delenv("PCF_TREE")
+    assert auto == (gpu.binom_vanilla_eur(*P, N, "put", warp_tiling=True).price,
+                    gpu.binom_vanilla_amer(*P, N, "put", warp_tiling=True).price)
     # full size (the reference needs 45 s per tree here): the European tree and the binomial formula price the same
     # lattice; early exercise is worth something for the put and nothing for the call (r > 0, no dividends)
     N = 100_000

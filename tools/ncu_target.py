@@ -1,4 +1,4 @@
-"""Profiling target (dev tool): `python tests/ncu_target.py <workload> <N> [reps]` runs one workload through
+"""Profiling target (dev tool): `python tools/ncu_target.py <workload> <N> [reps]` runs one workload through
 the C ABI so that ncu can capture its kernels. Not a test."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

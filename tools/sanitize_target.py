@@ -1,5 +1,5 @@
 """Dev tool: one small call of every kernel family, sized for compute-sanitizer (memcheck / racecheck / synccheck):
-   compute-sanitizer --tool memcheck python tests/sanitize_target.py"""
+   compute-sanitizer --tool memcheck python tools/sanitize_target.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

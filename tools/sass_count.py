@@ -1,5 +1,5 @@
 """Dev tool: instruction mix of a kernel's hottest loop from `cuobjdump -sass parcompfin_b200/libpcf.so`.
-usage: python tests/sass_count.py <mangled-name-fragment>   (prints the largest backward-branch loop's mix)"""
+usage: python tools/sass_count.py <mangled-name-fragment>   (prints the largest backward-branch loop's mix)"""
 import collections, re, subprocess, sys
 frag = sys.argv[1]
 txt = subprocess.check_output(["cuobjdump", "-sass", "parcompfin_b200/libpcf.so"]).decode()

@@ -1,4 +1,4 @@
-"""Profiling target (dev tool): `python tests/tree_target.py <eur|amer> <N> [reps]` runs one tree through the C ABI."""
+"""Profiling target (dev tool): `python tools/tree_target.py <eur|amer> <N> [reps]` runs one tree through the C ABI."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import parcompfin_b200 as pcf
