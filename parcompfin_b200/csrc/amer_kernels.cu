@@ -20,13 +20,12 @@
 // Rows and `when` are padded to a multiple of 16 paths (Np) with never-in-the-money dummies so that every TMA
 // bulk copy (rows and dates) is a whole number of 16-byte granules.
 //
-// Backward sweep: ONE fused kernel per exercise date. amer_sweep_kernel for date m (a) waits for the moments of
-// date m (its own, or -- multi-GPU -- every rank's, arriving in the NVLink mailbox), solves the 3x3 normal
-// equations per block in the reference's operation order without FMA contraction, (b) applies the exercise
-// decision of date m to the dates held in registers, (c) accumulates the regression moments of date m-1 from
-// that updated state and row m-1, and (d) its last block publishes them. The kernel of date 1 accumulates the
-// final discounted sum (mc_amer.cpp:109-111) instead of (c); the kernel of date M initialises the state
-// (mc_amer.cpp:23-27) instead of (a)-(b).
+// Backward sweep: ONE persistent kernel walks the exercise dates m = M .. 1. At date m every CTA (a) waits for the
+// moments of date m (every rank's, its own included, arriving in this GPU's mailbox), solves the 3x3 normal equations
+// in the reference's operation order without FMA contraction, (b) applies the exercise decision of date m to the dates
+// held in registers, (c) accumulates the regression moments of date m-1 from that updated state and row m-1, and
+// (d) the last CTA to finish publishes them. Date 1 accumulates the final discounted sum (mc_amer.cpp:109-111) instead
+// of (c); date M initialises the state (mc_amer.cpp:23-27) instead of (a)-(b). See the sweep section below.
 #include "common.cuh"
 #include "reduce.cuh"
 #include "rng.cuh"
@@ -38,8 +37,10 @@ namespace pcf {
 constexpr int kAmerBlock = 256;
 constexpr int kMaxDates = 2048;  // discount tables: constant memory -> staged into shared memory per block
 
-__constant__ double c_disc_fwd[kMaxDates + 1];  // exp(-r*dt*k)        as mc_amer.cpp:50 evaluates it
-__constant__ double c_disc_abs[kMaxDates + 1];  // exp(-r*k*dt)        as mc_amer.cpp:110 evaluates it
+// Per-call tables, ONE upload: [0, 64) the path kernel's (e^a 2^(j/32), e^a 2^(-j/32)) pairs, then M+1 factors
+// exp(-r*dt*k) as mc_amer.cpp:50 evaluates them, then M+1 factors exp(-r*k*dt) as mc_amer.cpp:110 does.
+constexpr int kDiscFwd = 2 * kExpEntries;
+__constant__ double c_amer_tab[kDiscFwd + 2 * (kMaxDates + 1)];
 
 struct AmerArgs {
   double S0, E;
@@ -57,8 +58,7 @@ struct AmerArgs {
 // exp((r-s^2/2)dt +- s w): x = s w is reduced once, x = (32k + j) ln2/32 + r, and
 //   e^{a+x} = 2^k  [e^a 2^{ j/32}] (C(r) + S(r)),   e^{a-x} = 2^-k [e^a 2^{-j/32}] (C(r) - S(r))
 // with C/S the even/odd parts of e^r (degree 6/5; |r| <= ln2/64). The bracketed factors come from a per-call
-// 32-entry table (c_amer_T, e^a folded in on the host), one LDS.128 per step: 15 FP64 for both exponentials.
-__constant__ double c_amer_T[2 * kExpEntries];  // (e^a 2^(j/32), e^a 2^(-j/32)), j = 0..31
+// 32-entry table (c_amer_tab[0..63], e^a folded in on the host), one LDS.128 per step: 15 FP64 for both exponentials.
 
 __device__ __forceinline__ void amer_step(double& Sp, double& Sm, double z, double cs, const Pair* __restrict__ s_T) {
   const double x = cs * z;
@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(kAmerBlock, kMinBlocks) amer_paths_kernel(Amer
   const TableView tv = stage_tables(tables, tab_smem);
   Pair* s_T = reinterpret_cast<Pair*>(tab_smem + kTableSmemBytes);
   for (int i = threadIdx.x; i < kExpEntries * kRep16; i += blockDim.x) {
-    s_T[i].x = c_amer_T[2 * (i / kRep16)];
-    s_T[i].y = c_amer_T[2 * (i / kRep16) + 1];
+    s_T[i].x = c_amer_tab[2 * (i / kRep16)];
+    s_T[i].y = c_amer_tab[2 * (i / kRep16) + 1];
   }
   __syncthreads();
   const Pair* my_T = s_T + (threadIdx.x & (kRep16 - 1));
@@ -203,17 +203,19 @@ __device__ bool solve3_reference_order(const double* mom, double coef[3]) {
   return true;
 }
 
-// a7 (mc_amer.cpp:41-106), one fused kernel per date; see the file header.
-//   kMoments: accumulate the moments of date m-1 (row m-1) after the decision of date m and publish them
-//   kFinal:   date 1 -- accumulate the discounted booked cash flows and their squares (mc_amer.cpp:109-111)
-//   first:    date M -- no decision (the state was initialised to when = M, mc_amer.cpp:23-27)
-// mom_out[0..7] = n_itm, Sx, Sx^2, Sx^3, Sx^4, Sy, Syx, Syx^2 with x = S - E, y = discounted cash flow; products
-// are formed exactly like the reference forms them (left to right, no FMA): only the summation order differs.
-//
-// Data movement: the two rows and the date array are streamed HBM -> shared memory by the TMA engine
-// (cp.async.bulk, one elected producer thread, kTilePaths paths per stage, `stages`-deep mbarrier ring), so the
-// bytes in flight per SM are set by the ring (stages x 17 KB per CTA), not by registers x resident warps; the
-// 8 consumer warps only see shared-memory latency plus the occasional gather.
+// ---- a7 (mc_amer.cpp:41-106): the backward sweep --------------------------------------------------------------
+// Two drivers share one per-quad body (sweep_quad):
+//   * amer_sweep_persistent_kernel: ONE cooperative launch walks all M dates (default: one GPU, and several GPUs with
+//     the NVLink mailboxes). Between two dates the grid meets at a split barrier: every CTA leaves its 8 compensated
+//     partial sums in global memory and takes a ticket; the CTA that takes the last one folds them in block order and
+//     publishes the moments of date m-1 to every rank's mailbox (its own included); every CTA then waits for all ranks'
+//     flags, adds the world x 8 values in rank order and solves the 3x3 system. While it waits, its producer warp has
+//     already refilled the TMA ring with the first tiles of rows m-1 / m-2 -- the bulk copies do not depend on the
+//     moments -- so a date boundary costs the barrier's latency, not a pipeline drain plus a kernel launch.
+//   * amer_sweep_kernel: one launch per date, used when the moments travel by ncclAllReduce between two kernels
+//     (PCF_NO_PEER / no peer mapping), and the round-1 baseline of the A/B measurement.
+// mom[0..7] = n_itm, Sx, Sx^2, Sx^3, Sx^4, Sy, Syx, Syx^2 with x = S - E, y = discounted cash flow; products are formed
+// exactly like the reference forms them (left to right, no FMA): only the summation order differs.
 constexpr int kMomFold = 16;  // tiles (64 paths per thread) between folds of the plain running sums
 constexpr int kTilePaths = 1024;
 constexpr int kSweepConsumers = 256;                    // 4 paths of every tile per consumer thread
@@ -235,8 +237,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Bounded: a protocol error must end in a trapped kernel (an error code on the host), never in a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -245,10 +249,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    if (!done && ++spins > (1u << 30)) __trap();
   } while (!done);
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar`; streamed data is marked evict-first in L2
-// (each row is read by two consecutive kernels 800 MB apart: no reuse to protect, and the gathers do hit L2)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
@@ -256,33 +260,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
-
-struct SweepArgs {
-  const double* paths;  // row m-1 = date m, stride Np
-  void* when;
-  long long Np;         // multiple of 16
-  double E;
-  int cp, m, M;
-  int rev;              // tiles are walked from the far end (alternate dates: the tail of the previous kernel's
-                        // row m-1 and date tiles is still in L2 when this kernel starts there)
-  int first;            // date M: no decision
-  int lsm;              // PCF_FLAG_AMER_LSM
-  int stages;
-  const double* mom_in;
-  double* partials;
-  unsigned int* ticket;
-  double* out;          // kMoments: the 8 moments of date m-1; kFinal: sum, sumsq
-  int* err_flag;
-};
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kSweepConsumers) : "memory"); }
 
 template <typename WT>
 __global__ void amer_fill_when_kernel(WT* __restrict__ when, long long Np, int M) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += (long long)gridDim.x * blockDim.x)
     when[i] = (WT)M;
 }
-
-template <typename WT>
-__host__ __device__ constexpr size_t sweep_stage_bytes() { return (size_t)kTilePaths * (8 + 8 + sizeof(WT)); }
 
 // Exercise dates of one quad of paths: uint8 x 4 (one 32-bit word) or uint16 x 4 (one 64-bit word).
 template <typename WT> struct WhenQuad;
@@ -307,29 +291,447 @@ template <> struct WhenQuad<uint16_t> {
   static __device__ __forceinline__ Vec splat(int d) { return make_uint2(0x00010001u * (uint32_t)d, 0x00010001u * (uint32_t)d); }
 };
 
-template <typename WT, bool kMoments, bool kFinal, bool kEarly, int kCtas>
-__global__ void __launch_bounds__(kSweepBlock, kCtas) amer_sweep_kernel(SweepArgs a, PeerLink link_in, PeerLink link_out) {
+// What every consumer thread needs to know about date m once its regression is solved.
+//   mode 0 skip (no path in the money, mc_amer.cpp:73), 1 few-paths branch (:75-83), 2 regression branch with the
+//   reference's rule (:97-106), 3 regression branch with the textbook rule (PCF_FLAG_AMER_LSM)
+struct DateRule {
+  int mode, booked;
+  double c0, c1s, c2, nE2, sentinel;
+};
+
+// Thread 0 of a CTA: moments of date m -> s_mode / s_coef (mc_amer.cpp:73-95, common.h:98-141)
+__device__ __forceinline__ void solve_date(const double* s_mom, int lsm, int* s_mode, double* s_coef, int* err_flag) {
+  const double cnt = s_mom[0];
+  if (cnt == 0.0) {
+    *s_mode = 0;                       // mc_amer.cpp:73
+  } else if (cnt <= 2.0) {
+    *s_mode = 1;                       // mc_amer.cpp:75
+  } else {
+    double coef[3];
+    if (solve3_reference_order(s_mom, coef)) {
+      *s_mode = lsm ? 3 : 2;
+      s_coef[0] = coef[0]; s_coef[1] = coef[1]; s_coef[2] = coef[2];
+    } else {
+      *s_mode = 0;
+      if (blockIdx.x == 0) *(volatile int*)err_flag = PCF_ESINGULAR;  // common.h:115-117 (host-mapped status word)
+    }
+  }
+}
+
+template <typename WT>
+__device__ __forceinline__ DateRule make_rule(int mode, const double* s_coef, double sgn, double nE, int m) {
+  // Everything works on cx = cp*(S - E) = fma(sgn, S, -sgn*E): bit-identical to the reference's (double)cp*(S - E)
+  // (negation is exact and rounding is symmetric), one DFMA. The regressor x = S - E is sgn*cx, so x^2, x^4 and y x^2
+  // are sign-free and Sx, Sx^3, Syx are sgn times the sums formed from cx.
+  // reference rule (mode 2): exercise when payoff(x, E) = max(cp*(x - E), 0) = max(cx + nE, 0) exceeds the fit
+  // (mc_amer.cpp:100), and a path with x == -1 collides with the reference's sentinel and is skipped
+  // (mc_amer.cpp:32,98). PCF_FLAG_AMER_LSM (mode 3): the true payoff cx, no sentinel, books without the flag.
+  DateRule R;
+  R.mode = mode;
+  R.c0 = s_coef[0];
+  R.c1s = s_coef[1] * sgn;  // c1*x == (c1*sgn)*cx exactly
+  R.c2 = s_coef[2];
+  R.nE2 = (mode == 2) ? nE : 0.0;
+  R.sentinel = (mode == 2) ? -sgn : __longlong_as_double(0x7ff8000000000000LL);
+  R.booked = (mode == 2) ? (m | WhenBits<WT>::kFlag) : m;
+  return R;
+}
+
+// One quad (4 consecutive paths, one 32-byte sector per row) at date m: the decision of date m on the dates w[], then
+// the terms of date m-1's moments (kMoments) or of the final sum (kFinal) added to run[] / cnt. Returns true when any of
+// the four dates changed. src = row m, sp = row m-1 (kMoments). colp + d*row_bytes is the address of paths[d][first path
+// of the quad]; s_disc[k] = exp(-r dt k), s_abs[k] = exp(-r k dt).
+template <typename WT, bool kMoments, bool kFinal>
+__device__ __forceinline__ bool sweep_quad(const double (&src)[4], const double (&sp)[4], int (&w)[4], bool live,
+                                           const DateRule& R, int m, double sgn, double nE,
+                                           const char* colp, size_t row_bytes, const double* s_disc,
+                                           const double* s_abs, double (&run)[8], int& cnt) {
+  constexpr int kFlag = WhenBits<WT>::kFlag, kMask = WhenBits<WT>::kMask;
+  const double* s_disc_m = s_disc - (m - 1);  // s_disc_m[d] = exp(-r dt (d - (m-1)))
+  // cp*(S_m - E), cp*(S_{m-1} - E)
+  double cx[4], ex[4], gv[4];
+  bool need[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    cx[e] = fma(sgn, src[e], nE);  // payoff(S_m) = max(cx, 0)
+    need[e] = live;
+    ex[e] = 0.0;
+    if (kMoments) {
+      const double c = fma(sgn, sp[e], nE);
+      need[e] = live && c > 0.0;
+      ex[e] = need[e] ? c : 0.0;
+    }
+    gv[e] = src[e];
+  }
+  // (b) decision of date m
+  bool changed = false;
+  if (R.mode >= 2) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double yhat = __dadd_rn(__dadd_rn(R.c0, __dmul_rn(R.c1s, cx[e])), __dmul_rn(R.c2, __dmul_rn(cx[e], cx[e])));
+      const double pq = __dadd_rn(cx[e], R.nE2);  // before the max(., 0): max(t, 0) > y <=> t > y | 0 > y
+      const bool exer = live & (cx[e] > 0.0) & (cx[e] != R.sentinel) & ((pq > yhat) | (0.0 > yhat));
+      w[e] = exer ? R.booked : w[e];
+      changed |= exer;
+    }
+  } else if (R.mode == 1 && live) {
+    // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against the discounted cash flow
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (cx[e] > 0.0) {
+        const int d = w[e] & kMask;
+        const double g = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
+        const double pg = fma(sgn, g, nE);  // payoff(g, E, cp) = max(cp*(g - E), 0), same rounding
+        const double cont = __dmul_rn(s_disc[d - m], pg > 0.0 ? pg : 0.0);
+        if (cx[e] > cont) {
+          w[e] = m;
+          changed = true;
+        }
+      }
+    }
+  }
+  // (c) gathers: the cash flow is needed (in the money at m-1, or the final sum) and the path did not exercise at m,
+  // so it comes from paths[when][n] (mc_amer.cpp:50) -- frequent under PCF_FLAG_AMER_LSM and for calls, rare for the
+  // reference rule's puts
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int d = w[e] & kMask;
+    if (need[e] && d != m)
+      gv[e] = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
+  }
+  // (d) moments of date m-1 / final sum. Out-of-the-money (and dead) lanes add exact zeros.
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int d = w[e] & kMask;
+    const double cr = fma(sgn, gv[e], nE);
+    const double cs = (need[e] && cr > 0.0) ? cr : 0.0;  // payoff(paths[when][n]), 0 when not needed
+    if (kMoments) {
+      const double x1 = ex[e];
+      const double cont = __dmul_rn(s_disc_m[d], cs);  // d >= m: index in [1, M]
+      const double x2 = __dmul_rn(x1, x1), x3 = __dmul_rn(x2, x1), x4 = __dmul_rn(x3, x1);
+      const double yx = __dmul_rn(cont, x1), yx2 = __dmul_rn(yx, x1);
+      cnt += need[e] ? 1 : 0;
+      run[1] += x1;
+      run[2] += x2;
+      run[3] += x3;
+      run[4] += x4;
+      run[5] += cont;
+      run[6] += yx;
+      run[7] += yx2;
+    }
+    if (kFinal) {
+      // exercise_st (mc_amer.cpp:103): the regression branch booked payoff(x, E) = max(cp*(x - E), 0), x = S - E;
+      // a flagged path has cs > 0, a dead lane has w = m (no flag) and cs = 0
+      const double sq = __dadd_rn(cs, nE);
+      const double stv = (w[e] & kFlag) ? (sq > 0.0 ? sq : 0.0) : cs;
+      const double v = __dmul_rn(s_abs[d], stv);
+      run[0] += v;
+      run[1] += v * v;
+    }
+  }
+  return changed;
+}
+
+// Fold of the plain per-thread runs (<= 4 kMomFold terms each): summed over the warp in a fixed shuffle order and added
+// to the warp's compensated totals in shared memory; only lane 0's copy is used.
+template <int kSums, bool kCount>
+__device__ __forceinline__ void fold_runs(double (&run)[8], int& cnt, double2 (*s_wacc)[8], int tid) {
+  if (kCount) run[0] = (double)cnt;
+  cnt = 0;
+#pragma unroll
+  for (int k = 0; k < kSums; ++k) {
+    double v = run[k];
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, dlt));
+    if ((tid & 31) == 0) {
+      const double2 t = s_wacc[tid >> 5][k];
+      Comp c(t.x, t.y);
+      c.add(v);
+      s_wacc[tid >> 5][k] = make_double2(c.hi, c.lo);
+    }
+    run[k] = 0.0;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Persistent driver: all dates in one cooperative launch.
+struct SweepPArgs {
+  const double* paths;  // row m-1 = date m, stride Np
+  void* when;
+  long long Np;         // multiple of 16
+  double E;
+  int cp, M, lsm;
+  double* partials;     // [grid][8][2]
+  unsigned int* ticket;
+  double* out;          // final (sum, sumsq), job-wide: host-mapped
+  int* err_flag;        // host-mapped status word
+  unsigned long long seq0;  // the iteration of date m publishes exchange seq0 + (M - m)
+};
+
+// State a consumer thread carries across the dates of the persistent kernel.
+template <typename WT>
+struct SweepCarry {
+  typename WhenQuad<WT>::Vec wnext;  // dates of the first tile of the coming date (held in registers, never re-read)
+  uint32_t it;                       // ring iterations so far: slot = it % kStages, phase = (it / kStages) & 1
+};
+
+// One date of the persistent kernel, consumer side: all tiles of this CTA at date m.
+template <typename WT, bool kFinal, int kStages>
+__device__ __forceinline__ void consume_date(const SweepPArgs& a, const DateRule& R, int m, int nk, SweepCarry<WT>& cy,
+                                             unsigned char* ring, uint64_t* s_full, uint64_t* s_empty,
+                                             const double* s_disc, double2 (*s_wacc)[8]) {
   typedef WhenQuad<WT> WQ;
   typedef typename WQ::Vec WVec;
-  constexpr int kFlag = WhenBits<WT>::kFlag, kMask = WhenBits<WT>::kMask;
+  constexpr size_t kStage = (size_t)kTilePaths * 16;
+  const int tid = threadIdx.x;
+  const int M = a.M;
+  const bool first = (m == M);
+  const bool rev = ((M - m) & 1) != 0;
+  const long long Np = a.Np;
+  const double sgn = (double)a.cp, nE = -sgn * a.E;
+  const size_t row_bytes = (size_t)Np * 8;
+  WT* when = reinterpret_cast<WT*>(a.when);
+  // address of paths[d][n] for this thread's first path of tile 0 is colp0 + d*row_bytes (row d-1 holds date d)
+  const char* colp0 = reinterpret_cast<const char*>(a.paths) + (size_t)tid * 32 - row_bytes;
+  double run[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) run[k] = 0.0;
+  int cnt = 0;
+  for (int kk = 0; kk < nk; ++kk) {
+    const long long t = blockIdx.x + (long long)(rev ? nk - 1 - kk : kk) * gridDim.x;
+    const long long c0t = t * kTilePaths;
+    const bool live = c0t + 4 * tid < Np;  // Np is a multiple of 16: a quad is live or dead as a whole
+    WVec* wp = reinterpret_cast<WVec*>(when + c0t) + tid;
+    WVec wv = cy.wnext;
+    if (kk + 1 < nk && !first) {
+      // dates of the NEXT tile: this thread's own store of the previous date, fetched one tile ahead
+      const long long c0n = (blockIdx.x + (long long)(rev ? nk - 2 - kk : kk + 1) * gridDim.x) * kTilePaths;
+      if (c0n + 4 * tid < Np) cy.wnext = __ldcg(reinterpret_cast<const WVec*>(when + c0n) + tid);
+    }
+    const uint32_t slot = cy.it % kStages, ph = (cy.it / kStages) & 1u;
+    ++cy.it;
+    const unsigned char* st = ring + (size_t)slot * kStage;
+    mbar_wait(&s_full[slot], ph);
+    const double2 sa = *reinterpret_cast<const double2*>(st + tid * 32);
+    const double2 sb = *reinterpret_cast<const double2*>(st + tid * 32 + 16);
+    double2 pa = make_double2(0.0, 0.0), pb = pa;
+    if (!kFinal) {
+      pa = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32);
+      pb = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32 + 16);
+    }
+    // generic-proxy reads of the slot must be ordered before the TMA engine (async proxy) refills it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&s_empty[slot]);
+    if (first) wv = WQ::splat(M);
+    if (!live) wv = WQ::splat(m);  // dead quad (tail of the last tile): date m, no flag, never in the money
+
+    const double src[4] = {sa.x, sa.y, sb.x, sb.y};
+    const double sp[4] = {pa.x, pa.y, pb.x, pb.y};
+    int w[4];
+    WQ::unpack(wv, w);
+    const char* colp = colp0 + (size_t)c0t * 8;
+    const bool changed = sweep_quad<WT, !kFinal, kFinal>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes, s_disc,
+                                                         s_disc + (M + 1), run, cnt);
+    const WVec wnew = WQ::pack(w);
+    if (first) {
+      if (live) *wp = wnew;                                           // mc_amer.cpp:23-27
+    } else if (R.mode >= 2) {
+      if (__any_sync(0xffffffffu, changed) && live) *wp = wnew;       // whole 128-byte lines back
+    } else if (changed) {
+      *wp = wnew;
+    }
+    if (kk + 1 == nk) cy.wnext = wnew;  // the coming date starts on this tile
+    if ((kk & (kMomFold - 1)) == kMomFold - 1) fold_runs<kFinal ? 2 : 8, !kFinal>(run, cnt, s_wacc, tid);
+  }
+  fold_runs<kFinal ? 2 : 8, !kFinal>(run, cnt, s_wacc, tid);
+}
+
+template <typename WT, int kStages>
+__global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persistent_kernel(SweepPArgs a, PeerLink link) {
+  constexpr size_t kStage = (size_t)kTilePaths * 16;  // row m + row m-1; the dates travel through registers
+  __shared__ double s_mom[kXchgVals];
+  __shared__ double s_coef[3];
+  __shared__ double s_red[kSweepConsumers / 32][2];
+  __shared__ double s_pub[kXchgVals + 8];
+  __shared__ int s_mode, s_last;
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+  __shared__ double2 s_wacc[kSweepConsumers / 32][8];  // per-WARP compensated totals of the current date
+  extern __shared__ __align__(128) unsigned char dyn[];
+  unsigned char* ring = dyn;                                                   // kStages x kStage
+  double* s_disc = reinterpret_cast<double*>(dyn + (size_t)kStages * kStage);  // exp(-r dt k), k = 0..M, then exp(-r k dt)
+  const int tid = threadIdx.x;
+  const int M = a.M;
+  for (int k = tid; k < 2 * (M + 1); k += blockDim.x) s_disc[k] = c_amer_tab[kDiscFwd + k];
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kSweepConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long Np = a.Np;
+  const long long ntiles = (Np + kTilePaths - 1) / kTilePaths;
+  // tiles blockIdx.x, blockIdx.x + grid, ...: the SAME tiles at every date, so a path's exercise date is only ever
+  // touched by one thread of one CTA (no cross-thread visibility to arrange) and the first tile of date m-1 is the last
+  // tile of date m (the walk alternates its direction), whose dates are still in registers and whose rows are in L2
+  const int nk = (blockIdx.x < ntiles) ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+
+  if (tid >= kSweepConsumers) {
+    // ---- producer warp: one elected lane keeps the ring full, across date boundaries
+    if (tid == kSweepConsumers) {
+      // row m is dead after this date (evict-first); row m-1 is read again at the next date, which starts where this
+      // one ends, so it keeps the default policy
+      uint64_t pol, pol_keep;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+      uint32_t it = 0;
+      for (int m = M; m >= 1; --m) {
+        const bool rev = ((M - m) & 1) != 0;
+        const double* row_m = a.paths + (size_t)(m - 1) * Np;
+        const double* row_p = a.paths + (size_t)(m > 1 ? m - 2 : 0) * Np;
+        for (int kk = 0; kk < nk; ++kk, ++it) {
+          const long long t = blockIdx.x + (long long)(rev ? nk - 1 - kk : kk) * gridDim.x;
+          const uint32_t slot = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(&s_empty[slot], ph ^ 1);
+          const long long c0 = t * kTilePaths;
+          const uint32_t n = (uint32_t)((Np - c0 < kTilePaths) ? (Np - c0) : kTilePaths);  // multiple of 16
+          unsigned char* st = ring + (size_t)slot * kStage;
+          mbar_arrive_expect_tx(&s_full[slot], n * (m > 1 ? 16u : 8u));
+          bulk_g2s(st, row_m + c0, n * 8u, &s_full[slot], pol);
+          if (m > 1) bulk_g2s(st + kTilePaths * 8, row_p + c0, n * 8u, &s_full[slot], pol_keep);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: thread `tid` owns paths 4 tid .. 4 tid + 3 of every tile (one 32-byte sector per row)
+  const double sgn = (double)a.cp, nE = -sgn * a.E;
+  SweepCarry<WT> cy;
+  cy.wnext = WhenQuad<WT>::splat(M);  // mc_amer.cpp:23-27: when = M
+  cy.it = 0;
+
+  for (int m = M; m >= 1; --m) {
+    const bool first = (m == M), final_date = (m == 1);
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_wacc[tid >> 5][k] = make_double2(0.0, 0.0);
+    }
+    if (!first) {
+      // moments of date m: every rank's publication (this GPU's own included) in this GPU's mailbox
+      if (tid < 32) peer_gather_warp<kXchgVals>(link, a.seq0 + (unsigned long long)(M - m - 1), s_mom);
+      consumer_bar();
+      if (tid == 0) solve_date(s_mom, a.lsm, &s_mode, s_coef, a.err_flag);
+    } else if (tid == 0) {
+      s_mode = 0;
+    }
+    consumer_bar();
+    const DateRule R = make_rule<WT>(s_mode, s_coef, sgn, nE, m);
+    if (final_date) consume_date<WT, true, kStages>(a, R, m, nk, cy, ring, s_full, s_empty, s_disc, s_wacc);
+    else consume_date<WT, false, kStages>(a, R, m, nk, cy, ring, s_full, s_empty, s_disc, s_wacc);
+    consumer_bar();
+
+    // ---- split grid barrier, arrival: CTA totals (one lane per moment, warps merged in order) -> global partials
+    if (tid < 32) {
+      if (tid < 8) {
+        Comp tot;
+#pragma unroll
+        for (int wq = 0; wq < kSweepConsumers / 32; ++wq) {
+          const double2 v = s_wacc[wq][tid];
+          tot.merge(Comp(v.x, v.y));
+        }
+        // back from cx-space to the reference's x = S - E: odd powers of x carry the sign of cp
+        const double f = (!final_date && (tid == 1 || tid == 3 || tid == 6)) ? sgn : 1.0;
+        a.partials[((size_t)blockIdx.x * 8 + tid) * 2 + 0] = tot.hi * f;
+        a.partials[((size_t)blockIdx.x * 8 + tid) * 2 + 1] = tot.lo * f;
+        __threadfence();
+      }
+      __syncwarp();
+      if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    consumer_bar();
+    if (s_last) {
+      // ---- the last CTA to arrive folds all partials in block order and publishes (reduce.cuh grid_reduce, restated
+      // for the 8 consumer warps: the producer warp is busy refilling the ring and takes no part in barriers)
+      __threadfence();
+      for (int k = 0; k < 8; ++k) {
+        Comp acc;
+        for (unsigned int b = tid; b < gridDim.x; b += kSweepConsumers) {
+          const volatile double* pp = a.partials + ((size_t)b * 8 + k) * 2;
+          acc.merge(Comp(pp[0], pp[1]));
+        }
+        acc = warp_reduce(acc);
+        if ((tid & 31) == 0) { s_red[tid >> 5][0] = acc.hi; s_red[tid >> 5][1] = acc.lo; }
+        consumer_bar();
+        if (tid == 0) {
+          Comp tot;
+#pragma unroll
+          for (int wq = 0; wq < kSweepConsumers / 32; ++wq) tot.merge(Comp(s_red[wq][0], s_red[wq][1]));
+          s_pub[k] = tot.value();
+        }
+        consumer_bar();
+      }
+      if (tid == 0) *a.ticket = 0u;
+      const unsigned long long seq_out = a.seq0 + (unsigned long long)(M - m);
+      peer_publish<kXchgVals>(link, seq_out, s_pub, consumer_bar);
+      if (final_date) {
+        consumer_bar();
+        if (tid < 32) peer_gather_warp<kXchgVals>(link, seq_out, s_pub + 8);
+        consumer_bar();
+        if (tid < 2) a.out[tid] = s_pub[8 + tid];
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Per-date driver (NCCL fallback path): one launch per exercise date; rows AND dates stream through the TMA ring.
+struct SweepArgs {
+  const double* paths;  // row m-1 = date m, stride Np
+  void* when;
+  long long Np;         // multiple of 16
+  double E;
+  int cp, m, M;
+  int rev;              // tiles are walked from the far end (alternate dates: the tail of the previous kernel's
+                        // row m-1 and date tiles is still in L2 when this kernel starts there)
+  int first;            // date M: no decision
+  int lsm;              // PCF_FLAG_AMER_LSM
+  int stages;
+  const double* mom_in;
+  double* partials;
+  unsigned int* ticket;
+  double* out;          // kMoments: the 8 moments of date m-1; kFinal: sum, sumsq
+  int* err_flag;
+};
+
+template <typename WT>
+__host__ __device__ constexpr size_t sweep_stage_bytes() { return (size_t)kTilePaths * (8 + 8 + sizeof(WT)); }
+
+template <typename WT, bool kMoments, bool kFinal>
+__global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_kernel(SweepArgs a, PeerLink link_out) {
+  typedef WhenQuad<WT> WQ;
+  typedef typename WQ::Vec WVec;
   constexpr size_t kStage = sweep_stage_bytes<WT>();
   constexpr int kSums = kFinal ? 2 : 8;
   __shared__ double smem[8 * 2 * 32];
   __shared__ double s_mom[kXchgVals];
   __shared__ double s_coef[3];
-  __shared__ int s_mode;  // 0 skip, 1 few-paths branch, 2 regression branch, 3 regression branch (LSM rule)
+  __shared__ int s_mode;
   __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages];
-  // per-WARP compensated totals (lane 0 of each consumer warp updates its row once per kMomFold tiles)
-  __shared__ double2 s_wacc[kSweepConsumers / 32][kSums];
+  __shared__ double2 s_wacc[kSweepConsumers / 32][8];
   extern __shared__ __align__(128) unsigned char dyn[];
   unsigned char* ring = dyn;                                                     // stages x kStage
   double* s_disc = reinterpret_cast<double*>(dyn + (size_t)a.stages * kStage);   // exp(-r dt k), k = 0..M
   double* s_abs = s_disc + (a.M + 1);                                            // exp(-r k dt) (kFinal)
   const int tid = threadIdx.x;
-  if (tid < (kSweepConsumers / 32) * kSums) s_wacc[tid / kSums][tid % kSums] = make_double2(0.0, 0.0);
+  if (tid < (kSweepConsumers / 32) * 8) s_wacc[tid / 8][tid % 8] = make_double2(0.0, 0.0);
   for (int k = tid; k <= a.M; k += blockDim.x) {
-    s_disc[k] = c_disc_fwd[k];
-    if (kFinal) s_abs[k] = c_disc_abs[k];
+    s_disc[k] = c_amer_tab[kDiscFwd + k];
+    s_abs[k] = c_amer_tab[kDiscFwd + (a.M + 1) + k];
   }
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
@@ -351,10 +753,8 @@ __global__ void __launch_bounds__(kSweepBlock, kCtas) amer_sweep_kernel(SweepArg
   WT* when = reinterpret_cast<WT*>(a.when);
 
   if (tid >= kSweepConsumers) {
-    // ---- producer warp: one elected lane keeps the ring full; it starts before the moments of date m arrive
+    // ---- producer warp: one elected lane keeps the ring full; it starts before the moments of date m are read
     if (tid == kSweepConsumers) {
-      // row m is dead after this kernel (evict-first); row m-1 and the dates are read again by the next kernel, which
-      // starts where this one ends (a.rev alternates), so they keep the default policy
       uint64_t pol, pol_keep;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
       asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
@@ -374,84 +774,30 @@ __global__ void __launch_bounds__(kSweepBlock, kCtas) amer_sweep_kernel(SweepArg
       }
     }
   } else {
-    // ---- consumers: thread `tid` owns paths 4 tid .. 4 tid + 3 of every tile (one 32-byte sector per row)
+    // ---- consumers
     if (!a.first) {
-      // moments of date m: from every rank's publication in this GPU's mailbox (multi-GPU), else local / all-reduced
-      if (link_in.world > 1) {
-        if (tid < 32) peer_gather_warp<kXchgVals>(link_in, s_mom);
-      } else if (tid < kXchgVals) {
-        s_mom[tid] = a.mom_in[tid];
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kSweepConsumers) : "memory");
-      if (tid == 0) {
-        const double cnt = s_mom[0];
-        if (cnt == 0.0) {
-          s_mode = 0;                       // mc_amer.cpp:73
-        } else if (cnt <= 2.0) {
-          s_mode = 1;                       // mc_amer.cpp:75
-        } else {
-          double coef[3];
-          if (solve3_reference_order(s_mom, coef)) {
-            s_mode = a.lsm ? 3 : 2;
-            s_coef[0] = coef[0]; s_coef[1] = coef[1]; s_coef[2] = coef[2];
-          } else {
-            s_mode = 0;
-            if (blockIdx.x == 0) atomicExch(a.err_flag, PCF_ESINGULAR);  // common.h:115-117
-          }
-        }
-      }
+      if (tid < kXchgVals) s_mom[tid] = a.mom_in[tid];  // all-reduced by NCCL between the two launches
+      consumer_bar();
+      if (tid == 0) solve_date(s_mom, a.lsm, &s_mode, s_coef, a.err_flag);
     } else if (tid == 0) {
       s_mode = 0;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kSweepConsumers) : "memory");
-    const int mode = s_mode;
-    // Everything below works on cx = cp*(S - E) = fma(sgn, S, -sgn*E): bit-identical to the reference's
-    // (double)cp*(S - E) (negation is exact and rounding is symmetric), one DFMA. The regressor x = S - E is
-    // sgn*cx, so x^2, x^4 and y x^2 are sign-free and Sx, Sx^3, Syx are sgn times the sums formed from cx.
+    consumer_bar();
     const double sgn = (double)cp, nE = -sgn * E;
-    const double c0 = s_coef[0], c1s = s_coef[1] * sgn, c2 = s_coef[2];  // c1*x == (c1*sgn)*cx exactly
-    // reference rule (mode 2): exercise when payoff(x, E) = max(cp*(x - E), 0) = max(cx + nE, 0) exceeds the fit
-    // (mc_amer.cpp:100), and a path with x == -1 collides with the reference's sentinel and is skipped
-    // (mc_amer.cpp:32,98). PCF_FLAG_AMER_LSM (mode 3): the true payoff cx, no sentinel, books without the flag.
-    const double nE2 = (mode == 2) ? nE : 0.0;
-    const double sentinel = (mode == 2) ? -sgn : __longlong_as_double(0x7ff8000000000000LL);
-    const int booked = (mode == 2) ? (m | kFlag) : m;
-
-    double run[kSums];
+    const DateRule R = make_rule<WT>(s_mode, s_coef, sgn, nE, m);
+    double run[8];
 #pragma unroll
-    for (int k = 0; k < kSums; ++k) run[k] = 0.0;
+    for (int k = 0; k < 8; ++k) run[k] = 0.0;
     int cnt = 0, fold = 0;
-    // Fold: the plain per-thread runs (<= 4 kMomFold terms each) are summed over the warp in a fixed shuffle order
-    // and added to the warp's compensated totals; only lane 0's copy is used.
-    auto fold_runs = [&]() {
-      if (kMoments) run[0] = (double)cnt;
-      cnt = 0;
-#pragma unroll
-      for (int k = 0; k < kSums; ++k) {
-        double v = run[k];
-#pragma unroll
-        for (int dlt = 16; dlt > 0; dlt >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, dlt));
-        if ((tid & 31) == 0) {
-          const double2 t = s_wacc[tid >> 5][k];
-          Comp c(t.x, t.y);
-          c.add(v);
-          s_wacc[tid >> 5][k] = make_double2(c.hi, c.lo);
-        }
-        run[k] = 0.0;
-      }
-    };
     const size_t row_bytes = (size_t)Np * 8;
-    const double* s_disc_m = s_disc - (m - 1);  // s_disc_m[d] = exp(-r dt (d - (m-1)))
-    // address of paths[d][n] for this thread's first path of tile 0 is colp0 + d*row_bytes (row d-1 holds date d)
     const char* colp0 = reinterpret_cast<const char*>(paths) + (size_t)tid * 32 - row_bytes;
-
     int s = 0;
     uint32_t ph = 0;
     for (long long tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
       const long long t = a.rev ? ntiles - 1 - tt : tt;
       const unsigned char* st = ring + (size_t)s * kStage;
       const long long c0t = t * kTilePaths;
-      const bool live = c0t + 4 * tid < Np;  // Np is a multiple of 16: a quad is live or dead as a whole
+      const bool live = c0t + 4 * tid < Np;
       mbar_wait(&s_full[s], ph);
       const double2 sa = *reinterpret_cast<const double2*>(st + tid * 32);
       const double2 sb = *reinterpret_cast<const double2*>(st + tid * 32 + 16);
@@ -467,108 +813,27 @@ __global__ void __launch_bounds__(kSweepBlock, kCtas) amer_sweep_kernel(SweepArg
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
       if (++s == a.stages) { s = 0; ph ^= 1; }
-      if (!live) wv = WQ::splat(m);  // dead quad (tail of the last tile): date m, no flag, never in the money
+      if (!live) wv = WQ::splat(m);
 
       const double src[4] = {sa.x, sa.y, sb.x, sb.y};
-      double sp[4] = {pa.x, pa.y, pb.x, pb.y};
+      const double sp[4] = {pa.x, pa.y, pb.x, pb.y};
       int w[4];
       WQ::unpack(wv, w);
       WVec* wp = reinterpret_cast<WVec*>(when + c0t) + tid;
       const char* colp = colp0 + (size_t)c0t * 8;
-      // (a') cp*(S_m - E), cp*(S_{m-1} - E) and the gathers that are certain: a path out of the money at m cannot
-      // exercise at m, so if its cash flow is needed (in the money at m-1, or the final sum) it comes from
-      // paths[when][n] (mc_amer.cpp:50) with the date it already has. Issued before the decision arithmetic so
-      // that the DRAM round trip overlaps it.
-      double cx[4], ex[4], gv[4];
-      bool need[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        cx[e] = fma(sgn, src[e], nE);  // payoff(S_m) = max(cx, 0)
-        need[e] = live;
-        ex[e] = 0.0;
-        if (kMoments) {
-          const double c = fma(sgn, sp[e], nE);
-          need[e] = live && c > 0.0;
-          ex[e] = need[e] ? c : 0.0;
-        }
-        gv[e] = src[e];
-        if (kEarly && need[e] && !(cx[e] > 0.0))
-          gv[e] = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)(w[e] & kMask) * row_bytes) + e);
-      }
-      // (b) decision of date m
-      if (mode >= 2) {
-        bool changed = false;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const double yhat = __dadd_rn(__dadd_rn(c0, __dmul_rn(c1s, cx[e])), __dmul_rn(c2, __dmul_rn(cx[e], cx[e])));
-          const double pq = __dadd_rn(cx[e], nE2);  // before the max(., 0): max(t, 0) > y <=> t > y | 0 > y
-          const bool exer = live & (cx[e] > 0.0) & (cx[e] != sentinel) & ((pq > yhat) | (0.0 > yhat));
-          w[e] = exer ? booked : w[e];
-          changed |= exer;
-        }
-        // whole 128-byte lines back: a warp stores its 128 dates when any of them changed
+      const bool changed = sweep_quad<WT, kMoments, kFinal>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes,
+                                                            s_disc, s_abs, run, cnt);
+      if (R.mode >= 2) {
         if (__any_sync(0xffffffffu, changed) && live) *wp = WQ::pack(w);
-      } else if (mode == 1 && live) {
-        // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against the discounted cash flow
-        bool changed = false;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (cx[e] > 0.0) {
-            const int d = w[e] & kMask;
-            const double g = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
-            const double cont = __dmul_rn(s_disc[d - m], payoff(g, E, cp));
-            if (cx[e] > cont) {
-              w[e] = m;
-              changed = true;
-            }
-          }
-        }
-        if (changed) *wp = WQ::pack(w);
-      }
-      // (c) the remaining gathers: in the money at m, cash flow needed, yet not exercised at m (frequent under
-      // PCF_FLAG_AMER_LSM and for calls, never for the reference rule's puts)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int d = w[e] & kMask;
-        if (need[e] && (!kEarly || cx[e] > 0.0) && d != m)
-          gv[e] = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
-      }
-      // (d) moments of date m-1 / final sum. Out-of-the-money (and dead) lanes add exact zeros.
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int d = w[e] & kMask;
-        const double cr = fma(sgn, gv[e], nE);
-        const double cs = (need[e] && cr > 0.0) ? cr : 0.0;  // payoff(paths[when][n]), 0 when not needed
-        if (kMoments) {
-          const double x1 = ex[e];
-          const double cont = __dmul_rn(s_disc_m[d], cs);  // d >= m: index in [1, M]
-          const double x2 = __dmul_rn(x1, x1), x3 = __dmul_rn(x2, x1), x4 = __dmul_rn(x3, x1);
-          const double yx = __dmul_rn(cont, x1), yx2 = __dmul_rn(yx, x1);
-          cnt += need[e] ? 1 : 0;
-          run[1] += x1;
-          run[2] += x2;
-          run[3] += x3;
-          run[4] += x4;
-          run[5] += cont;
-          run[6] += yx;
-          run[7] += yx2;
-        }
-        if (kFinal) {
-          // exercise_st (mc_amer.cpp:103): the regression branch booked payoff(x, E) = max(cp*(x - E), 0), x = S - E;
-          // a flagged path has cs > 0, a dead lane has w = m (no flag) and cs = 0
-          const double sq = __dadd_rn(cs, nE);
-          const double stv = (w[e] & kFlag) ? (sq > 0.0 ? sq : 0.0) : cs;
-          const double v = __dmul_rn(s_abs[d], stv);
-          run[0] += v;
-          run[1] += v * v;
-        }
+      } else if (changed) {
+        *wp = WQ::pack(w);
       }
       if (++fold == kMomFold) {
-        fold_runs();
+        fold_runs<kSums, kMoments>(run, cnt, s_wacc, tid);
         fold = 0;
       }
     }
-    fold_runs();
+    fold_runs<kSums, kMoments>(run, cnt, s_wacc, tid);
   }
   // warp totals -> block -> grid (block_reduce's own first stage sees one meaningful lane per warp)
   Comp acc[kSums];
@@ -581,7 +846,6 @@ __global__ void __launch_bounds__(kSweepBlock, kCtas) amer_sweep_kernel(SweepArg
   }
   if (kMoments) {
     const double sgn = (double)cp;
-    // back from cx-space to the reference's x = S - E: odd powers of x carry the sign of cp
     acc[1].hi *= sgn; acc[1].lo *= sgn;
     acc[3].hi *= sgn; acc[3].lo *= sgn;
     acc[6].hi *= sgn; acc[6].lo *= sgn;
@@ -590,59 +854,55 @@ __global__ void __launch_bounds__(kSweepBlock, kCtas) amer_sweep_kernel(SweepArg
   grid_reduce<kSums>(acc, smem, a.partials, a.ticket, a.out, &link_out);
 }
 
-template <typename WT, bool kEarly, int kCtas>
-static int launch_sweep2(Ctx& c, bool final_date, int grid, int stages, const SweepArgs& a, const PeerLink& li,
-                         const PeerLink& lo) {
+template <typename WT>
+static int launch_sweep(Ctx& c, bool final_date, int grid, int stages, const SweepArgs& a, const PeerLink& lo) {
   const size_t dsm = (size_t)stages * sweep_stage_bytes<WT>() + 2 * sizeof(double) * (a.M + 1);
   if (final_date) {
-    auto k = amer_sweep_kernel<WT, false, true, kEarly, kCtas>;
+    auto k = amer_sweep_kernel<WT, false, true>;
     PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-    k<<<grid, kSweepBlock, dsm, c.stream>>>(a, li, lo);
+    k<<<grid, kSweepBlock, dsm, c.stream>>>(a, lo);
   } else {
-    auto k = amer_sweep_kernel<WT, true, false, kEarly, kCtas>;
+    auto k = amer_sweep_kernel<WT, true, false>;
     PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-    k<<<grid, kSweepBlock, dsm, c.stream>>>(a, li, lo);
+    k<<<grid, kSweepBlock, dsm, c.stream>>>(a, lo);
   }
   return PCF_OK;
 }
-template <typename WT>
-static int launch_sweep(Ctx& c, bool final_date, int grid, int stages, int per_sm, bool early, const SweepArgs& a,
-                        const PeerLink& li, const PeerLink& lo) {
-#ifdef PCF_TUNING
-  if (per_sm >= 3) {
-    return early ? launch_sweep2<WT, true, 3>(c, final_date, grid, stages, a, li, lo)
-                 : launch_sweep2<WT, false, 3>(c, final_date, grid, stages, a, li, lo);
+
+template <typename WT, int kStages>
+static int launch_sweep_persistent(Ctx& c, const SweepPArgs& a, const PeerLink& link, long long ntiles) {
+  auto k = amer_sweep_persistent_kernel<WT, kStages>;
+  const size_t dsm = (size_t)kStages * kTilePaths * 16 + 2 * sizeof(double) * (a.M + 1);
+  PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+  int per_sm = 0;
+  PCF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kSweepBlock, dsm));
+  if (per_sm < 1) {
+    set_last_error("mc_amer: the sweep kernel does not fit on this device");
+    return PCF_ECUDA;
   }
-  return early ? launch_sweep2<WT, true, 2>(c, final_date, grid, stages, a, li, lo)
-               : launch_sweep2<WT, false, 2>(c, final_date, grid, stages, a, li, lo);
-#else
-  (void)per_sm; (void)early;
-  return launch_sweep2<WT, false, kSweepCtasPerSM>(c, final_date, grid, stages, a, li, lo);
-#endif
+  // every CTA must be resident for the in-kernel date barrier: cooperative launch, grid <= what the device holds
+  long long grid = std::min<long long>(ntiles, (long long)c.sm_count * std::min(per_sm, kSweepCtasPerSM));
+  if (grid < 1) grid = 1;  // an empty shard still takes part in every exchange
+  SweepPArgs args = a;
+  PeerLink l = link;
+  void* params[] = {(void*)&args, (void*)&l};
+  PCF_CUDA(cudaLaunchCooperativeKernel((const void*)k, dim3((unsigned)grid), dim3(kSweepBlock), params, dsm, c.stream));
+  return PCF_OK;
 }
 
 static inline size_t amer_when_bytes(int M) { return M <= WhenBits<uint8_t>::kMask ? 1 : 2; }
 
-// Host driver for one GPU. Enqueues everything on c.stream; result (sum, sumsq of discounted cash
-// flows over local paths) lands in c.d_out[0..1]; c.d_out[8..23] holds the per-date moment vectors.
-int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset,
-                PeerLink* final_link) {
+// Host driver for one GPU. Enqueues everything on c.stream; the job-wide (sum, sumsq) of the discounted cash flows lands
+// in final_out(c)[0..1] (NCCL path: this GPU's partial sums in c.d_out[0..1]); c.d_out[8..23] holds the per-date moment
+// vectors of the per-date chain.
+int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset) {
   const int M = p.M;
   if (M > kMaxDates) {
-    set_last_error("mc_amer: M exceeds kMaxDates");
+    set_last_error("mc_amer: M exceeds 2048 exercise dates (include/pcf.h)");
     return PCF_EINVAL;
   }
   const long long H = pairs.size(), Nl = 2 * H;
   const double dt = p.T / M;
-  // discount tables, evaluated on the host with the reference's own expressions (glibc exp)
-  static thread_local double fwd[kMaxDates + 1], ab[kMaxDates + 1];
-  for (int k = 0; k <= M; ++k) {
-    fwd[k] = exp(-p.r * dt * (double)k);  // exp(-r*dt*(exercise_when[n]-m))   mc_amer.cpp:50
-    ab[k] = exp(-p.r * (double)k * dt);   // exp(-r*exercise_when[n]*dt)       mc_amer.cpp:110
-  }
-  PCF_CUDA(cudaMemcpyToSymbolAsync(c_disc_fwd, fwd, sizeof(double) * (M + 1), 0, cudaMemcpyHostToDevice, c.stream));
-  PCF_CUDA(cudaMemcpyToSymbolAsync(c_disc_abs, ab, sizeof(double) * (M + 1), 0, cudaMemcpyHostToDevice, c.stream));
-
   const long long Np = (Nl + 15) & ~15LL;  // padded row length: 128-byte rows, 16-byte date tiles (TMA granules)
   char* base = (char*)c.workspace + ws_offset;
   double* paths = (double*)base;
@@ -655,14 +915,20 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   a.p0 = pairs.begin; a.H = H; a.Np = Np; a.seed = p.seed; a.w = d_replay;
 
   {
-    // per-call table: e^a 2^(+-j/32), a = (r - sigma^2/2) dt, in long double then rounded once
-    double Tt[2 * kExpEntries];
+    static thread_local double tab[kDiscFwd + 2 * (kMaxDates + 1)];
+    // path kernel: e^a 2^(+-j/32), a = (r - sigma^2/2) dt, in long double then rounded once
     const long double ea = expl((long double)a.adt);
     for (int j = 0; j < kExpEntries; ++j) {
-      Tt[2 * j] = (double)(ea * exp2l((long double)j / kExpEntries));
-      Tt[2 * j + 1] = (double)(ea * exp2l(-(long double)j / kExpEntries));
+      tab[2 * j] = (double)(ea * exp2l((long double)j / kExpEntries));
+      tab[2 * j + 1] = (double)(ea * exp2l(-(long double)j / kExpEntries));
     }
-    PCF_CUDA(cudaMemcpyToSymbolAsync(c_amer_T, Tt, sizeof(Tt), 0, cudaMemcpyHostToDevice, c.stream));
+    // discount tables, evaluated on the host with the reference's own expressions (glibc exp)
+    for (int k = 0; k <= M; ++k) {
+      tab[kDiscFwd + k] = exp(-p.r * dt * (double)k);            // exp(-r*dt*(exercise_when[n]-m))   mc_amer.cpp:50
+      tab[kDiscFwd + (M + 1) + k] = exp(-p.r * (double)k * dt);  // exp(-r*exercise_when[n]*dt)       mc_amer.cpp:110
+    }
+    PCF_CUDA(cudaMemcpyToSymbolAsync(c_amer_tab, tab, sizeof(double) * (kDiscFwd + 2 * (M + 1)), 0,
+                                     cudaMemcpyHostToDevice, c.stream));
   }
   const size_t gen_smem = kTableSmemBytes + (size_t)kExpEntries * kRep16 * sizeof(Pair);
   if (d_replay) {
@@ -700,20 +966,44 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   }
   PCF_CUDA(cudaGetLastError());
 
-  // Backward sweep m = M .. 1 (mc_amer.cpp:23-27, 31, 109-111). Kernel for date m consumes the moments of date m
-  // and produces those of date m-1. Peer path: moments travel through the NVLink mailboxes (publish in the
-  // producing kernel, gather in the consuming one); NCCL path: an all-reduce of the 8 doubles between two kernels.
-  // Launch shape: PCF_AMER_SWEEP = "<ring stages>,<CTAs per SM>,<early gathers 0|1>" (PCF_TUNING builds).
-  int stages = 2, per_sm = kSweepCtasPerSM, early = 0;
-  if (const char* v = tuning_env("PCF_AMER_SWEEP")) {
-    if (sscanf(v, "%d,%d,%d", &stages, &per_sm, &early) != 3 || stages < 2 || stages > kMaxStages || per_sm < 1 || per_sm > kSweepCtasPerSM) {
-      set_last_error("bad PCF_AMER_SWEEP");
-      return PCF_EINVAL;
-    }
-  }
+  // Backward sweep m = M .. 1 (mc_amer.cpp:23-27, 31, 109-111). The iteration of date m consumes the moments of date m
+  // and produces those of date m-1 (date 1: the final sums).
   const long long ntiles = (Np + kTilePaths - 1) / kTilePaths;
-  const int grid = (int)std::min<long long>(ntiles, (long long)c.sm_count * per_sm);
   const bool w8 = amer_when_bytes(M) == 1;
+  const bool nccl_path = c.world > 1 && !use_peer(c);
+  const bool chain = nccl_path || tuning_env("PCF_AMER_CHAIN") != nullptr;
+  int stages = 2;
+  if (const char* v = tuning_env("PCF_AMER_SWEEP")) stages = std::max(2, std::min(kMaxStages, atoi(v)));
+  if (!chain) {
+    // ONE cooperative launch; moments travel through the mailboxes (this GPU's own when it is alone)
+    SweepPArgs sp;
+    sp.paths = paths; sp.when = when; sp.Np = Np; sp.E = p.E; sp.cp = p.cp; sp.M = M;
+    sp.lsm = (p.flags & PCF_FLAG_AMER_LSM) ? 1 : 0;
+    sp.partials = c.d_partials; sp.ticket = c.d_ticket; sp.out = c.res_dev; sp.err_flag = c.flag_dev;
+    sp.seq0 = c.xchg_seq + 1;
+    c.xchg_seq += (unsigned long long)M;  // M exchanges, whether or not other ranks exist
+    PeerLink l = c.link;
+    l.host_err = c.perr_dev;
+    l.gather = 0;
+    l.seq = 0;
+    l.call_first = c.call_first;
+    l.call_last = c.call_last;
+    if (c.world <= 1) { l.world = 1; l.rank = 0; l.peer[0] = c.mailbox; }
+#ifdef PCF_TUNING
+    if (stages == 3) {
+      if (w8) PCF_TRY((launch_sweep_persistent<uint8_t, 3>(c, sp, l, ntiles)));
+      else PCF_TRY((launch_sweep_persistent<uint16_t, 3>(c, sp, l, ntiles)));
+    } else
+#endif
+    if (w8) PCF_TRY((launch_sweep_persistent<uint8_t, 2>(c, sp, l, ntiles)));
+    else PCF_TRY((launch_sweep_persistent<uint16_t, 2>(c, sp, l, ntiles)));
+    c.launches++;
+    PCF_CUDA(cudaGetLastError());
+    return PCF_OK;
+  }
+  // Per-date chain: an all-reduce of the 8 doubles between two launches (NCCL), or -- PCF_AMER_CHAIN in a tuning build,
+  // one GPU -- the round-1 baseline of the persistent kernel.
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)c.sm_count * kSweepCtasPerSM));
   {
     const int fg = grid_for(c, Np, 256, 8);
     if (w8) amer_fill_when_kernel<uint8_t><<<fg, 256, 0, c.stream>>>((uint8_t*)when, Np, M);
@@ -724,23 +1014,20 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   sa.paths = paths; sa.when = when; sa.Np = Np; sa.E = p.E; sa.cp = p.cp; sa.M = M;
   sa.lsm = (p.flags & PCF_FLAG_AMER_LSM) ? 1 : 0;
   sa.stages = stages;
-  sa.partials = c.d_partials; sa.ticket = c.d_ticket; sa.err_flag = c.d_flag;
+  sa.partials = c.d_partials; sa.ticket = c.d_ticket; sa.err_flag = c.flag_dev;
   double* mom[2] = {c.d_out + 8, c.d_out + 16};
   PeerLink none = c.link;
   none.world = 1;
-  PeerLink l_in = none;
+  none.gather = 0;
   for (int m = M; m >= 1; --m) {
     sa.m = m;
     sa.first = (m == M);
     sa.rev = (M - m) & 1;
     sa.mom_in = mom[m & 1];
-    if (m < M && !use_peer(c)) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));
-    const PeerLink l_out = next_link(c);
-    sa.out = (m > 1) ? mom[(m - 1) & 1] : c.d_out;
-    if (w8) PCF_TRY(launch_sweep<uint8_t>(c, m == 1, grid, stages, per_sm, early != 0, sa, l_in, l_out));
-    else PCF_TRY(launch_sweep<uint16_t>(c, m == 1, grid, stages, per_sm, early != 0, sa, l_in, l_out));
-    if (m == 1) *final_link = l_out;
-    l_in = l_out;
+    if (m < M) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));
+    sa.out = (m > 1) ? mom[(m - 1) & 1] : final_out(c);
+    if (w8) PCF_TRY(launch_sweep<uint8_t>(c, m == 1, grid, stages, sa, none));
+    else PCF_TRY(launch_sweep<uint16_t>(c, m == 1, grid, stages, sa, none));
     c.launches++;
   }
   PCF_CUDA(cudaGetLastError());

@@ -203,7 +203,7 @@ static int basket_launch(Ctx& c, K kernel, const BasketArgs& a, long long paths,
   int per_sm = 0;
   PCF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, kTableSmemBytes));
   const int grid = grid_for(c, (paths + per_thread - 1) / per_thread, kBlock, per_sm > 0 ? per_sm : 1);
-  kernel<<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+  kernel<<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, final_out(c));
   return PCF_OK;
 }
 
@@ -291,7 +291,7 @@ int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host /* d*d row-m
   case P * 10 + B: {                                                                                       \
     int grid = grid_for(c, (paths.size() + P - 1) / P, kBlock, B);                                         \
     mc_basket_equi_kernel<P, B><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, \
-                                                                            c.d_ticket, c.d_out);          \
+                                                                            c.d_ticket, final_out(c));          \
   } break;
     switch (variant) {
 #ifdef PCF_TUNING

@@ -53,16 +53,23 @@ __global__ void __launch_bounds__(kBinomBlock, 4) binom_terms_kernel(BinomArgs a
   grid_reduce<1>(v, smem, partials, ticket, out, &link);
 }
 
-// `pairs` = this GPU's slice of i in [lo, until); result (partial undiscounted sum) -> c.d_out[0].
+// d(0..15), the Stirling-error table of stirlerr(): parameter-independent, uploaded once per context (pcf_api.cu ctx_open)
+int upload_binom_tables(Ctx& c) {
+  BinomArgs a;
+  fill_binom_args(100.0, 100.0, 0.05, 0.2, 1.0, 1000, 1, a);
+  PCF_CUDA(cudaMemcpyToSymbol(c_sfe, a.sfe, sizeof(a.sfe), 0, cudaMemcpyHostToDevice));
+  return PCF_OK;
+}
+
+// `pairs` = this GPU's slice of i in [lo, until); result (partial undiscounted sum) -> final_out(c)[0].
 int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid, const PeerLink& link) {
   BinomArgs a;
   fill_binom_args(p.S0, p.E, p.r, p.sigma, p.T, p.N, p.cp, a);
   a.i0 = pairs.begin; a.i1 = pairs.end; a.add_mid = add_mid ? 1 : 0;
   a.screen = (p.flags & PCF_FLAG_BINOM_NOSCREEN) ? 0 : 1;
-  PCF_CUDA(cudaMemcpyToSymbolAsync(c_sfe, a.sfe, sizeof(a.sfe), 0, cudaMemcpyHostToDevice, c.stream));
   int grid = grid_for(c, pairs.size(), kBinomBlock, 4);
   binom_terms_kernel<<<grid, kBinomBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket,
-                                                                      c.d_out);
+                                                                      final_out(c));
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;

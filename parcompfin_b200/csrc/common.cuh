@@ -39,6 +39,12 @@ inline const char* tuning_env(const char*) { return nullptr; }
 constexpr int kMaxBlocks = 148 * 16;  // upper bound on any reduction grid
 constexpr int kMaxMoments = 8;
 
+struct HostOut {
+  double vals[8];
+  int flag;        // device-raised status (PCF_ESINGULAR), 0 = none
+  int peer_error;  // the peer-memory exchange timed out or was poisoned
+};
+
 // One context = one GPU of the job (one per process under torchrun, `gpus` of them in the
 // single-process front ends).
 struct Ctx {
@@ -50,10 +56,14 @@ struct Ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double* d_partials = nullptr;    // kMaxBlocks * kMaxMoments * 2 doubles
   unsigned int* d_ticket = nullptr;
-  double* d_out = nullptr;         // small result vector (64 doubles)
-  int* d_flag = nullptr;           // device-side error flag
+  double* d_out = nullptr;         // small device scratch vector (64 doubles): per-date moments of mc_amer, KAT output
   const MathTables* d_tables = nullptr;  // fastmath.cuh lookup tables (global memory; staged to smem per block)
-  double* h_out = nullptr;         // pinned mirror of d_out
+  // Results and status words live in host-MAPPED pinned memory: the last block of the reducing kernel writes them
+  // straight into host memory, so a call ends with one stream synchronise and no device-to-host copy.
+  HostOut* h_res = nullptr;        // host view
+  double* res_dev = nullptr;       // device alias of h_res->vals
+  int* flag_dev = nullptr;         // device alias of h_res->flag  (PCF_ESINGULAR raised by the sweep kernel)
+  int* perr_dev = nullptr;         // device alias of h_res->peer_error (xchg.cuh: timeout / poisoned mailbox)
   void* workspace = nullptr;       // grow-only scratch (mc_amer path store, replay streams)
   size_t workspace_bytes = 0;
   int launches = 0;                // kernels launched in the current call
@@ -63,12 +73,18 @@ struct Ctx {
   PeerLink link{};
   bool peer_ok = false;
   unsigned long long xchg_seq = 0;
+  unsigned long long call_first = 0, call_last = 0;  // sequence numbers owned by the call in flight
 };
 
 // Link for the next exchange of this call sequence (every rank issues the same sequence of exchanges).
 // Without peer mapping the returned link has world == 1, which turns publishing and gathering off.
-inline PeerLink next_link(Ctx& c) {
+// `gather`: the publishing block also collects every rank's sums (end-of-run moments).
+inline PeerLink next_link(Ctx& c, bool gather = true) {
   PeerLink l = c.link;
+  l.host_err = c.perr_dev;
+  l.gather = gather ? 1 : 0;
+  l.call_first = c.call_first;
+  l.call_last = c.call_last;
   if (c.world > 1 && c.peer_ok) {
     l.seq = ++c.xchg_seq;
   } else {
@@ -78,7 +94,10 @@ inline PeerLink next_link(Ctx& c) {
   return l;
 }
 inline bool use_peer(const Ctx& c) { return c.world > 1 && c.peer_ok; }
-int launch_xchg_finish(Ctx& c, const PeerLink& l, int k, double* d_out);  // d_out[0..k) = sum over ranks
+// Where a method's last block writes its end-of-run sums: host-mapped memory, except on the NCCL fallback path, whose
+// all-reduce runs in place on a device buffer.
+inline double* final_out(Ctx& c) { return (c.world > 1 && !c.peer_ok) ? c.d_out : c.res_dev; }
+int launch_xchg_poison(Ctx& c);  // raises `error` in every peer's mailbox
 
 int ctx_reserve(Ctx& c, size_t bytes);  // ensures c.workspace >= bytes
 int allreduce_sum(Ctx& c, double* d_buf, int count);  // in place, on c.stream; no-op if world == 1

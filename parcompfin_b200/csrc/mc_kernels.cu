@@ -79,7 +79,7 @@ int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay,
   const bool small = fabs(a.drift) + fabs(a.sigma * a.sqrtT) * kZMax <= kSmallExpBound;
   if (d_replay) {
     int grid = grid_for(c, pairs.size(), kBlock, 2);
-    mc_eur_kernel<true, false, 1, 2><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+    mc_eur_kernel<true, false, 1, 2><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, final_out(c));
   } else {
     const char* v = tuning_env("PCF_EUR_VARIANT");  // <pairs per thread><CTAs per SM> (PCF_TUNING builds)
     const int variant = v ? atoi(v) : 81;
@@ -87,9 +87,9 @@ int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay,
   case P * 10 + B: {                                                                                              \
     int grid = grid_for(c, (pairs.size() + P - 1) / P, kBlock, B);                                                \
     if (small)                                                                                                    \
-      mc_eur_kernel<false, true, P, B><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out); \
+      mc_eur_kernel<false, true, P, B><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, final_out(c)); \
     else                                                                                                          \
-      mc_eur_kernel<false, false, P, B><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out); \
+      mc_eur_kernel<false, false, P, B><<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, final_out(c)); \
   } break;
     switch (variant) {
 #ifdef PCF_TUNING
@@ -230,7 +230,7 @@ template <bool kSmallExp, int kPaths, int kMinBlocks>
 static void launch_asia(Ctx& c, const AsiaArgs& a, long long paths, const PeerLink& link) {
   int grid = grid_for(c, (paths + kPaths - 1) / kPaths, kBlock, kMinBlocks);
   mc_asia_kernel<kSmallExp, kPaths, kMinBlocks><<<grid, kBlock, kTableSmemBytes, c.stream>>>(
-      a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+      a, c.d_tables, link, c.d_partials, c.d_ticket, final_out(c));
 }
 
 int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay, const PeerLink& link) {
@@ -248,7 +248,7 @@ int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay
   const bool small = fabs(a.adt) + fabs(a.cs) * kZMax <= kSmallExpBound;
   if (d_replay) {
     int grid = grid_for(c, paths.size(), kBlock, kBlocksPerSM);
-    mc_asia_replay_kernel<<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, c.d_out);
+    mc_asia_replay_kernel<<<grid, kBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket, final_out(c));
   } else {
     // launch shape: PCF_ASIA_VARIANT = <paths per thread><min blocks per SM>, e.g. "14", "23" (PCF_TUNING builds)
     const char* v = tuning_env("PCF_ASIA_VARIANT");
@@ -286,16 +286,23 @@ int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay
 }
 
 // ------------------------------------------------------------------------------------------------
-// One-warp finisher of a peer-memory exchange: waits for every rank's flag, adds in rank order.
-__global__ void xchg_finish_kernel(PeerLink link, int k, double* out) {
-  __shared__ double s[kXchgVals];
-  peer_gather<kXchgVals>(link, s);
-  if ((int)threadIdx.x < k) out[threadIdx.x] = s[threadIdx.x];
+// A rank whose host failed before it could launch its kernels tells its peers: their waits fall through at once
+// (xchg.cuh) instead of running into the timeout.
+__global__ void xchg_poison_kernel(PeerLink link) {
+  const int t = threadIdx.x;
+  if (t < link.world && t != link.rank) {
+    *(volatile unsigned long long*)&link.peer[t]->poison_hi = link.call_last;
+    __threadfence_system();
+    *(volatile unsigned long long*)&link.peer[t]->poison_lo = link.call_first;
+    __threadfence_system();
+  }
 }
 
-int launch_xchg_finish(Ctx& c, const PeerLink& l, int k, double* d_out) {
-  xchg_finish_kernel<<<1, 32, 0, c.stream>>>(l, k, d_out);
-  c.launches++;
+int launch_xchg_poison(Ctx& c) {
+  PeerLink l = c.link;
+  l.call_first = c.call_first;
+  l.call_last = c.call_last;
+  xchg_poison_kernel<<<1, 32, 0, c.stream>>>(l);
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
 }

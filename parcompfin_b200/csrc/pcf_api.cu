@@ -29,8 +29,7 @@ int run_mc_eur(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay,
 int run_mc_asia(Ctx& c, const pcf_params& p, Shard paths, const double* d_replay, const PeerLink& link);
 int run_mc_basket(Ctx& c, const pcf_params& p, const double* L_host, Shard paths, const double* d_replay,
                   const PeerLink& link, const BasketHost* spec);
-int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset,
-                PeerLink* final_link);
+int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay, size_t ws_offset);
 size_t amer_workspace_bytes(long long local_pairs, int M);
 int run_binom_tree(Ctx& c, const pcf_params& p, bool american);
 int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid, const PeerLink& link);
@@ -40,6 +39,7 @@ int run_normal_stream(Ctx& c, uint64_t seed, uint32_t stream, uint64_t index0, l
 int run_fp64_peak(Ctx& c, double seconds_target, double* dfma_per_sec);
 int run_hbm_peak(Ctx& c, long long bytes, double* bytes_per_sec);
 void build_math_tables(MathTables& t);
+int upload_binom_tables(Ctx& c);
 
 // ---- error text --------------------------------------------------------------------------------
 static std::mutex g_err_mu;
@@ -99,7 +99,11 @@ static int nccl_load() {
   } while (0)
 
 int allreduce_sum(Ctx& c, double* d_buf, int count) {
-  if (c.world <= 1 || !c.comm) return PCF_OK;
+  if (c.world <= 1) return PCF_OK;
+  if (!c.comm) {
+    set_last_error("multi-GPU job without peer mapping or NCCL communicator");
+    return PCF_ENOINIT;
+  }
   PCF_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, c.comm, c.stream));
   return PCF_OK;
 }
@@ -119,11 +123,20 @@ static int ctx_open(Ctx& c, int device, int rank, int world) {
   PCF_CUDA(cudaMalloc(&c.d_partials, sizeof(double) * kMaxBlocks * kMaxMoments * 2));
   PCF_CUDA(cudaMalloc(&c.d_ticket, sizeof(unsigned int)));
   PCF_CUDA(cudaMalloc(&c.d_out, sizeof(double) * 64));
-  PCF_CUDA(cudaMalloc(&c.d_flag, sizeof(int)));
   PCF_CUDA(cudaMemset(c.d_ticket, 0, sizeof(unsigned int)));
   PCF_CUDA(cudaMemset(c.d_out, 0, sizeof(double) * 64));
-  PCF_CUDA(cudaMemset(c.d_flag, 0, sizeof(int)));
-  PCF_CUDA(cudaMallocHost(&c.h_out, sizeof(double) * 64));
+  {
+    void* h = nullptr;
+    PCF_CUDA(cudaHostAlloc(&h, sizeof(HostOut), cudaHostAllocMapped | cudaHostAllocPortable));
+    std::memset(h, 0, sizeof(HostOut));
+    c.h_res = (HostOut*)h;
+    void* d = nullptr;
+    PCF_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+    HostOut* dv = (HostOut*)d;
+    c.res_dev = dv->vals;
+    c.flag_dev = &dv->flag;
+    c.perr_dev = &dv->peer_error;
+  }
   PCF_CUDA(cudaMalloc(&c.mailbox, sizeof(Mailbox)));
   PCF_CUDA(cudaMemset(c.mailbox, 0, sizeof(Mailbox)));
   c.link = PeerLink{};
@@ -139,6 +152,7 @@ static int ctx_open(Ctx& c, int device, int rank, int world) {
   PCF_CUDA(cudaMalloc(&dt, sizeof(MathTables)));
   PCF_CUDA(cudaMemcpy(dt, &host_tables, sizeof(MathTables), cudaMemcpyHostToDevice));
   c.d_tables = dt;
+  PCF_TRY(upload_binom_tables(c));  // Stirling-error table of the binomial kernel: constant, uploaded once per context
   return PCF_OK;
 }
 
@@ -151,9 +165,8 @@ static void ctx_close(Ctx& c) {
   if (c.mailbox) cudaFree(c.mailbox);
   if (c.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.comm);
   if (c.workspace) cudaFree(c.workspace);
-  if (c.h_out) cudaFreeHost(c.h_out);
+  if (c.h_res) cudaFreeHost(c.h_res);
   if (c.d_tables) cudaFree((void*)c.d_tables);
-  if (c.d_flag) cudaFree(c.d_flag);
   if (c.d_out) cudaFree(c.d_out);
   if (c.d_ticket) cudaFree(c.d_ticket);
   if (c.d_partials) cudaFree(c.d_partials);
@@ -212,29 +225,45 @@ static int upload_replay(Ctx& c, const double* host, long long off, long long le
   return PCF_OK;
 }
 
-// Common tail of every method: [allreduce of k doubles] -> event -> D2H -> sync.
-static int finish_call(Ctx& c, const PeerLink& link, int k, double* host_vals, double* seconds_kernel, int* flag) {
-  if (c.world > 1) {
-    if (use_peer(c)) PCF_TRY(launch_xchg_finish(c, link, k, c.d_out));  // waits on the mailbox flags, adds in rank order
-    else if (c.comm) PCF_TRY(allreduce_sum(c, c.d_out, k));
-    else { set_last_error("multi-GPU job without peer mapping or NCCL communicator"); return PCF_ENOINIT; }
+// Brackets the device work of one call on one context. Every rank consumes the same `n_exch` exchange sequence numbers
+// whether or not its own call succeeds, and a rank that fails tells its peers (xchg.cuh poison range), so one rank's
+// ENOMEM neither hangs the others nor desynchronises the next call.
+template <class F>
+static int guarded_call(Ctx& c, int n_exch, F body) {
+  const unsigned long long seq0 = c.xchg_seq;
+  c.call_first = seq0 + 1;
+  c.call_last = seq0 + (unsigned long long)n_exch;
+  c.h_res->flag = 0;
+  c.h_res->peer_error = 0;
+  c.launches = 0;
+  int s = body();
+  if (use_peer(c)) {
+    c.xchg_seq = c.call_last;
+    if (s != PCF_OK) {
+      cudaGetLastError();
+      if (launch_xchg_poison(c) == PCF_OK) cudaStreamSynchronize(c.stream);
+    }
   }
+  return s;
+}
+
+// Common tail of every method: [NCCL all-reduce of k doubles + D2H on the fallback path] -> event -> sync. On the
+// default path the kernel's last block has already written the job-wide sums into host-mapped memory (reduce.cuh).
+static int finish_call(Ctx& c, int k, double* host_vals, double* seconds_kernel, int* flag) {
+  const bool nccl_path = c.world > 1 && !use_peer(c);
+  if (nccl_path) PCF_TRY(allreduce_sum(c, c.d_out, k));
   PCF_CUDA(cudaEventRecord(c.ev1, c.stream));
-  PCF_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * k, cudaMemcpyDeviceToHost, c.stream));
-  int hflag = 0, perr = 0;
-  PCF_CUDA(cudaMemcpyAsync(&hflag, c.d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  if (use_peer(c)) PCF_CUDA(cudaMemcpyAsync(&perr, &c.mailbox->error, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  if (nccl_path) PCF_CUDA(cudaMemcpyAsync(c.h_res->vals, c.d_out, sizeof(double) * k, cudaMemcpyDeviceToHost, c.stream));
   PCF_CUDA(cudaStreamSynchronize(c.stream));
-  if (perr) {
-    set_last_error("peer-memory exchange timed out waiting for another GPU");
+  if (c.h_res->peer_error) {
+    set_last_error("peer-memory exchange: a GPU of the job failed or did not answer within the timeout");
     return PCF_ENCCL;
   }
-  for (int i = 0; i < k; ++i) host_vals[i] = c.h_out[i];
+  for (int i = 0; i < k; ++i) host_vals[i] = c.h_res->vals[i];
   float ms = 0.f;
   PCF_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
   *seconds_kernel = ms * 1e-3;
-  *flag = hflag;
-  if (hflag) PCF_CUDA(cudaMemsetAsync(c.d_flag, 0, sizeof(int), c.stream));
+  *flag = c.h_res->flag;
   return PCF_OK;
 }
 
@@ -253,6 +282,28 @@ static int check_common(const pcf_params* p, pcf_result* out) {
   if (g_ctx.empty()) return PCF_ENOINIT;
   return PCF_OK;
 }
+
+// The kernels' exponentials scale by 2^k through the exponent field and assume |x| stays inside exp()'s finite range
+// (fastmath.cuh). A parameter set whose largest possible argument |drift| + |vol| * zmax leaves it -- where the reference
+// would print inf, 0 or NaN -- is refused here instead of being priced wrongly. zmax: the largest |z| the Philox stream
+// can produce (8.5), or the largest |w| of the caller's replay stream.
+static int check_exp_range(double drift, double vol, double zmax) {
+  const double x = std::fabs(drift) + std::fabs(vol) * zmax;
+  if (!(x <= 700.0)) {  // also catches NaN / inf parameters
+    set_last_error("parameters put exp() arguments up to " + std::to_string(x) + " in play (limit 700)");
+    return PCF_EINVAL;
+  }
+  return PCF_OK;
+}
+static double replay_absmax(const double* w, long long n) {
+  double m = 0.0;
+  for (long long i = 0; i < n; ++i) {
+    const double a = std::fabs(w[i]);
+    if (!(a <= m)) m = a;  // NaN propagates
+  }
+  return m;
+}
+constexpr double kHostZMax = 8.5;  // rng.cuh kZMax
 
 static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -275,6 +326,19 @@ static void fill_mc_result(pcf_result* out, const std::vector<CallOut>& co, doub
   out->seconds_total = now_s() - t0;
 }
 
+// Builds the NCCL communicator of a single-process job on first need (pcf_init maps the mailboxes instead when it can).
+static int ensure_comm_all() {
+  if (g_ctx.size() <= 1 || g_ctx[0].comm) return PCF_OK;
+  PCF_TRY(nccl_load());
+  const int gpus = (int)g_ctx.size();
+  std::vector<void*> comms(gpus);
+  std::vector<int> devs(gpus);
+  for (int i = 0; i < gpus; ++i) devs[i] = g_ctx[i].device;
+  PCF_NCCL(g_nccl.CommInitAll(comms.data(), gpus, devs.data()));
+  for (int i = 0; i < gpus; ++i) g_ctx[i].comm = comms[i];
+  return PCF_OK;
+}
+
 }  // namespace pcf
 
 using namespace pcf;
@@ -291,7 +355,11 @@ int pcf_init(int gpus) {
     set_last_error(std::string("no CUDA device: ") + cudaGetErrorString(e));
     return PCF_ECUDA;
   }
-  if (gpus <= 0 || gpus > ndev) gpus = (gpus <= 0) ? ndev : ndev;
+  if (gpus > ndev) {  // reference src/mc_eur_mpi.cpp:58-62: fail loudly at init
+    set_last_error("pcf_init: " + std::to_string(gpus) + " GPUs requested, " + std::to_string(ndev) + " visible");
+    return PCF_EINVAL;
+  }
+  if (gpus <= 0) gpus = ndev;
   g_ctx.resize(gpus);
   for (int i = 0; i < gpus; ++i) {
     int s = ctx_open(g_ctx[i], i, i, gpus);
@@ -316,18 +384,8 @@ int pcf_init(int gpus) {
         g_ctx[i].peer_ok = true;
       }
     } else {
-      int s = nccl_load();
+      int s = ensure_comm_all();
       if (s != PCF_OK) { pcf_shutdown(); return s; }
-      std::vector<void*> comms(gpus);
-      std::vector<int> devs(gpus);
-      for (int i = 0; i < gpus; ++i) devs[i] = i;
-      int r = g_nccl.CommInitAll(comms.data(), gpus, devs.data());
-      if (r != 0) {
-        set_last_error(std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r));
-        pcf_shutdown();
-        return PCF_ENCCL;
-      }
-      for (int i = 0; i < gpus; ++i) g_ctx[i].comm = comms[i];
     }
   }
   return PCF_OK;
@@ -399,6 +457,15 @@ int pcf_ipc_import(const unsigned char* handles, int world) {
 
 int pcf_peer_enable(int on) {
   if (g_ctx.empty()) return PCF_ENOINIT;
+  if (!on && g_ctx[0].world > 1) {
+    // switching to ncclAllReduce needs a communicator: built here for a single-process job; a one-process-per-GPU job
+    // must have passed an NCCL id to pcf_init_rank
+    if (g_ctx.size() > 1) PCF_TRY(ensure_comm_all());
+    if (!g_ctx[0].comm) {
+      set_last_error("pcf_peer_enable(0): no NCCL communicator (pcf_init_rank was called without an NCCL id)");
+      return PCF_ENOINIT;
+    }
+  }
   for (auto& c : g_ctx) {
     bool mapped = true;
     for (int r = 0; r < c.world; ++r) mapped = mapped && c.link.peer[r] != nullptr;
@@ -421,25 +488,29 @@ int pcf_world_size(void) { return g_ctx.empty() ? 0 : g_ctx[0].world; }
 int pcf_mc_eur(const pcf_params* p, pcf_result* out) {
   int s = check_common(p, out);
   if (s == PCF_OK && p->replay && p->replay_len < p->N) s = PCF_EINVAL;
+  if (s == PCF_OK)
+    s = p->replay ? check_exp_range((p->r - p->sigma * p->sigma / 2) * p->T, p->sigma, replay_absmax(p->replay, p->N))
+                  : check_exp_range((p->r - p->sigma * p->sigma / 2) * p->T, p->sigma * std::sqrt(p->T), kHostZMax);
   if (s != PCF_OK) { if (out) out->status = s; return s; }
   const double t0 = now_s();
   const long long pairs = (p->N + 1) / 2;
   std::vector<CallOut> co(g_ctx.size());
   s = for_each_ctx([&](Ctx& c) -> int {
     CallOut& o = co[&c - &g_ctx[0]];
-    c.launches = 0;
-    Shard sh = shard_of(pairs, c.rank, c.world);
-    const double* d_rep = nullptr;
-    if (p->replay) {
-      long long off = 2 * sh.begin, end = std::min(p->N, 2 * sh.end);
-      PCF_TRY(upload_replay(c, p->replay, off, end - off, 0, &d_rep));
-    }
-    PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
-    const PeerLink l = next_link(c);
-    PCF_TRY(run_mc_eur(c, *p, sh, d_rep, l));
-    PCF_TRY(finish_call(c, l, 2, o.vals, &o.seconds_kernel, &o.flag));
-    o.launches = c.launches;
-    return PCF_OK;
+    return guarded_call(c, 1, [&]() -> int {
+      Shard sh = shard_of(pairs, c.rank, c.world);
+      const double* d_rep = nullptr;
+      if (p->replay) {
+        long long off = 2 * sh.begin, end = std::min(p->N, 2 * sh.end);
+        PCF_TRY(upload_replay(c, p->replay, off, end - off, 0, &d_rep));
+      }
+      PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+      const PeerLink l = next_link(c);
+      PCF_TRY(run_mc_eur(c, *p, sh, d_rep, l));
+      PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+      o.launches = c.launches;
+      return PCF_OK;
+    });
   });
   if (s == PCF_OK) fill_mc_result(out, co, std::exp(-p->r * p->T), p->N, p->N, t0);
   out->status = s;
@@ -450,21 +521,27 @@ int pcf_mc_asia(const pcf_params* p, pcf_result* out) {
   int s = check_common(p, out);
   if (s == PCF_OK && p->M <= 0) s = PCF_EINVAL;
   if (s == PCF_OK && p->replay && p->replay_len < p->N * (long long)p->M) s = PCF_EINVAL;
+  if (s == PCF_OK) {
+    const double dt = p->T / p->M, adt = (p->r - p->sigma * p->sigma / 2) * dt;
+    s = p->replay ? check_exp_range(adt, p->sigma, replay_absmax(p->replay, p->N * (long long)p->M))
+                  : check_exp_range(adt, p->sigma * std::sqrt(dt), kHostZMax);
+  }
   if (s != PCF_OK) { if (out) out->status = s; return s; }
   const double t0 = now_s();
   std::vector<CallOut> co(g_ctx.size());
   s = for_each_ctx([&](Ctx& c) -> int {
     CallOut& o = co[&c - &g_ctx[0]];
-    c.launches = 0;
-    Shard sh = shard_of(p->N, c.rank, c.world);
-    const double* d_rep = nullptr;
-    if (p->replay) PCF_TRY(upload_replay(c, p->replay, sh.begin * p->M, sh.size() * p->M, 0, &d_rep));
-    PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
-    const PeerLink l = next_link(c);
-    PCF_TRY(run_mc_asia(c, *p, sh, d_rep, l));
-    PCF_TRY(finish_call(c, l, 2, o.vals, &o.seconds_kernel, &o.flag));
-    o.launches = c.launches;
-    return PCF_OK;
+    return guarded_call(c, 1, [&]() -> int {
+      Shard sh = shard_of(p->N, c.rank, c.world);
+      const double* d_rep = nullptr;
+      if (p->replay) PCF_TRY(upload_replay(c, p->replay, sh.begin * p->M, sh.size() * p->M, 0, &d_rep));
+      PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+      const PeerLink l = next_link(c);
+      PCF_TRY(run_mc_asia(c, *p, sh, d_rep, l));
+      PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+      o.launches = c.launches;
+      return PCF_OK;
+    });
   });
   if (s == PCF_OK) fill_mc_result(out, co, std::exp(-p->r * p->T), p->N, p->N * (long long)p->M, t0);
   out->status = s;
@@ -491,21 +568,34 @@ int pcf_chol_equicorr(int d, double rho, double* L) {
 
 // Shared driver of the two basket entry points. `spec` == nullptr: the reference's basket.
 static int basket_call(const pcf_params* p, const double* L, const BasketHost* spec, pcf_result* out) {
+  {
+    // largest exponent in play: |drift_a| + sigma_a * sum_k |A[a][k]| * zmax
+    const int d = p->assets;
+    const double zmax = p->replay ? replay_absmax(p->replay, p->N * (long long)d) : kHostZMax;
+    for (int a = 0; a < d; ++a) {
+      double rowsum = 0;
+      for (int k = 0; k < d; ++k) rowsum += std::fabs(L[a * d + k]);
+      const double sg = spec ? spec->sigma[a] : p->sigma;
+      int s = check_exp_range((p->r - sg * sg / 2) * p->T, sg * rowsum, zmax);
+      if (s != PCF_OK) { out->status = s; return s; }
+    }
+  }
   const double t0 = now_s();
   std::vector<CallOut> co(g_ctx.size());
   int s = for_each_ctx([&](Ctx& c) -> int {
     CallOut& o = co[&c - &g_ctx[0]];
-    c.launches = 0;
-    Shard sh = shard_of(p->N, c.rank, c.world);
-    const double* d_rep = nullptr;
-    if (p->replay)
-      PCF_TRY(upload_replay(c, p->replay, sh.begin * p->assets, sh.size() * p->assets, 0, &d_rep));
-    PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
-    const PeerLink l = next_link(c);
-    PCF_TRY(run_mc_basket(c, *p, L, sh, d_rep, l, spec));
-    PCF_TRY(finish_call(c, l, 2, o.vals, &o.seconds_kernel, &o.flag));
-    o.launches = c.launches;
-    return PCF_OK;
+    return guarded_call(c, 1, [&]() -> int {
+      Shard sh = shard_of(p->N, c.rank, c.world);
+      const double* d_rep = nullptr;
+      if (p->replay)
+        PCF_TRY(upload_replay(c, p->replay, sh.begin * p->assets, sh.size() * p->assets, 0, &d_rep));
+      PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+      const PeerLink l = next_link(c);
+      PCF_TRY(run_mc_basket(c, *p, L, sh, d_rep, l, spec));
+      PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+      o.launches = c.launches;
+      return PCF_OK;
+    });
   });
   if (s == PCF_OK) fill_mc_result(out, co, std::exp(-p->r * p->T), p->N, p->N, t0);
   out->status = s;
@@ -655,24 +745,29 @@ int pcf_mc_amer(const pcf_params* p, pcf_result* out) {
   if (s == PCF_OK && p->M <= 0) s = PCF_EINVAL;
   if (s == PCF_OK && (p->N % 2) != 0) s = PCF_EODD_N;  // reference include/common.h:180
   if (s == PCF_OK && p->replay && p->replay_len < (p->N / 2) * (long long)p->M) s = PCF_EINVAL;
+  if (s == PCF_OK) {
+    const double dt = p->T / p->M, adt = (p->r - p->sigma * p->sigma / 2) * dt;
+    s = p->replay ? check_exp_range(adt, p->sigma, replay_absmax(p->replay, (p->N / 2) * (long long)p->M))
+                  : check_exp_range(adt, p->sigma * std::sqrt(dt), kHostZMax);
+  }
   if (s != PCF_OK) { if (out) out->status = s; return s; }
   const double t0 = now_s();
   const long long pairs = p->N / 2;
   std::vector<CallOut> co(g_ctx.size());
   s = for_each_ctx([&](Ctx& c) -> int {
     CallOut& o = co[&c - &g_ctx[0]];
-    c.launches = 0;
-    Shard sh = shard_of(pairs, c.rank, c.world);
-    const size_t rep_bytes = p->replay ? (((size_t)sh.size() * p->M * 8 + 255) / 256) * 256 + 256 : 0;
-    PCF_TRY(ctx_reserve(c, rep_bytes + amer_workspace_bytes(sh.size(), p->M)));
-    const double* d_rep = nullptr;
-    if (p->replay) PCF_TRY(upload_replay(c, p->replay, sh.begin * p->M, sh.size() * p->M, 0, &d_rep));
-    PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
-    PeerLink l;
-    PCF_TRY(run_mc_amer(c, *p, sh, d_rep, rep_bytes, &l));
-    PCF_TRY(finish_call(c, l, 2, o.vals, &o.seconds_kernel, &o.flag));
-    o.launches = c.launches;
-    return PCF_OK;
+    return guarded_call(c, p->M, [&]() -> int {
+      Shard sh = shard_of(pairs, c.rank, c.world);
+      const size_t rep_bytes = p->replay ? (((size_t)sh.size() * p->M * 8 + 255) / 256) * 256 + 256 : 0;
+      PCF_TRY(ctx_reserve(c, rep_bytes + amer_workspace_bytes(sh.size(), p->M)));
+      const double* d_rep = nullptr;
+      if (p->replay) PCF_TRY(upload_replay(c, p->replay, sh.begin * p->M, sh.size() * p->M, 0, &d_rep));
+      PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+      PCF_TRY(run_mc_amer(c, *p, sh, d_rep, rep_bytes));
+      PCF_TRY(finish_call(c, 2, o.vals, &o.seconds_kernel, &o.flag));
+      o.launches = c.launches;
+      return PCF_OK;
+    });
   });
   if (s == PCF_OK) {
     for (auto& c : co)
@@ -706,15 +801,16 @@ int pcf_binom_embar(const pcf_params* p, pcf_result* out) {
   std::vector<CallOut> co(g_ctx.size());
   s = for_each_ctx([&](Ctx& c) -> int {
     CallOut& o = co[&c - &g_ctx[0]];
-    c.launches = 0;
-    Shard sh = shard_of(until - lo, c.rank, c.world);
-    sh.begin += lo; sh.end += lo;
-    PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
-    const PeerLink l = next_link(c);
-    PCF_TRY(run_binom(c, *p, sh, (p->N % 2 == 0) && c.rank == 0, l));
-    PCF_TRY(finish_call(c, l, 1, o.vals, &o.seconds_kernel, &o.flag));
-    o.launches = c.launches;
-    return PCF_OK;
+    return guarded_call(c, 1, [&]() -> int {
+      Shard sh = shard_of(until - lo, c.rank, c.world);
+      sh.begin += lo; sh.end += lo;
+      PCF_CUDA(cudaEventRecord(c.ev0, c.stream));
+      const PeerLink l = next_link(c);
+      PCF_TRY(run_binom(c, *p, sh, (p->N % 2 == 0) && c.rank == 0, l));
+      PCF_TRY(finish_call(c, 1, o.vals, &o.seconds_kernel, &o.flag));
+      o.launches = c.launches;
+      return PCF_OK;
+    });
   });
   if (s == PCF_OK) {
     out->sum = co[0].vals[0];
@@ -745,13 +841,12 @@ static int binom_tree_call(const pcf_params* p, pcf_result* out, bool american) 
   s = [&]() -> int {
     PCF_CUDA(cudaSetDevice(c.device));
     c.launches = 0;
-    PCF_TRY(run_binom_tree(c, *p, american));  // records c.ev0 after the pow tables are resident
+    PCF_TRY(run_binom_tree(c, *p, american));  // records c.ev0 after the pow tables are resident; root -> c.h_res (pinned)
     PCF_CUDA(cudaEventRecord(c.ev1, c.stream));
-    PCF_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     PCF_CUDA(cudaStreamSynchronize(c.stream));
     float ms = 0.f;
     PCF_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
-    o.vals[0] = c.h_out[0];
+    o.vals[0] = c.h_res->vals[0];
     o.seconds_kernel = ms * 1e-3;
     o.launches = c.launches;
     return PCF_OK;

@@ -93,7 +93,10 @@ __device__ __forceinline__ void block_reduce(Comp (&v)[K], double* smem) {
 // `ticket` must be zero on entry and is reset to zero on exit, so the buffer is reusable across
 // launches on the same stream. smem as for block_reduce.
 // When `link` names a multi-GPU job (world > 1) the last block also publishes the K sums to every peer's mailbox
-// (xchg.cuh): the reduction and the collective are one kernel.
+// (xchg.cuh): the reduction and the collective are one kernel. With link->gather set it then waits for every rank's
+// publication and overwrites out[k] with the job-wide sums (added in rank order: bit-identical on every GPU) -- the
+// end-of-run all-reduce of the reference (src/mc_eur_mpi.cpp:36) without a second launch. `out` may be host-mapped
+// pinned memory: the host reads the result right after the stream synchronises, no device-to-host copy.
 template <int K>
 __device__ __forceinline__ void grid_reduce(Comp (&v)[K], double* smem, double* partials,
                                             unsigned int* ticket, double* out, const PeerLink* link = nullptr) {
@@ -135,6 +138,11 @@ __device__ __forceinline__ void grid_reduce(Comp (&v)[K], double* smem, double* 
   if (link != nullptr && link->world > 1) {
     __syncthreads();
     peer_publish<K>(*link, smem);
+    if (link->gather) {
+      __syncthreads();
+      peer_gather<K>(*link, smem + 16);
+      if ((int)threadIdx.x < K) out[threadIdx.x] = smem[16 + threadIdx.x];
+    }
   }
 }
 

@@ -328,8 +328,8 @@ static int tree_launch_all(Ctx& c, TreeArgs a, long long N, bool amer, double* b
     n -= steps;
     std::swap(in, out);
   }
-  // root -> c.d_out[0]
-  PCF_CUDA(cudaMemcpyAsync(c.d_out, in, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  // root -> c.h_res->vals[0] (pinned)
+  PCF_CUDA(cudaMemcpyAsync(c.h_res->vals, in, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
 }
@@ -435,7 +435,7 @@ static int tree_launch_cta(Ctx& c, TreeArgs a, long long N, bool amer, double* b
     n -= steps;
     std::swap(in, out);
   }
-  PCF_CUDA(cudaMemcpyAsync(c.d_out, in, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  PCF_CUDA(cudaMemcpyAsync(c.h_res->vals, in, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
 }
@@ -459,7 +459,7 @@ static void pow_tables(double u, double d, long long N, double* out_u, double* o
 
 size_t tree_workspace_bytes(long long N) { return 4 * ((size_t)(N + 1) * sizeof(double) + 256); }
 
-// Enqueues the whole tree on c.stream; root value -> c.d_out[0]. The pow tables are uploaded BEFORE c.ev0 is recorded
+// Enqueues the whole tree on c.stream; root value -> c.h_res->vals[0]. The pow tables are uploaded BEFORE c.ev0 is recorded
 // (inputs resident when the device clock starts); the host clock of the call covers them.
 int run_binom_tree(Ctx& c, const pcf_params& p, bool american) {
   const long long N = p.N;

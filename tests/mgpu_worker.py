@@ -15,6 +15,12 @@ out["amer"] = pcf.mc_amer(*P1, 1_000_002, 50, "put", seed=31).price
 out["amer_call"] = pcf.mc_amer(100, 110, 0.02, 0.75, 1, 200_000, 20, "call", seed=31).price
 out["binom"] = pcf.binom(*P1, 1_000_001, "call").price
 out["amer_repeat"] = pcf.mc_amer(*P1, 1_000_002, 50, "put", seed=31).price
+# fewer units than ranks: trailing ranks hold an EMPTY shard and must still take part in every exchange
+out["amer_tiny"] = pcf.mc_amer(*P1, 2, 5, "put", seed=31).price
+out["asia_tiny"] = pcf.mc_asia(*P1, 1, 7, "call", seed=31).price
+out["eur_tiny"] = pcf.mc_eur(*P1, 1, "put", seed=31).price
+out["binom_tiny"] = pcf.binom(*P1, 1, "call").price
+out["amer_lsm"] = pcf.mc_amer(*P1, 400_000, 50, "put", seed=31, lsm=True).price
 if job.rank == 0:
     print("MGPU " + json.dumps(out), flush=True)
 dist.barrier(job)

@@ -526,6 +526,23 @@ def test_error_behaviour(gpu):
         gpu.mc_eur(*P1, 100, "call", replay=np.zeros(50))      # replay stream too short
     with pytest.raises(ValueError):
         gpu.mc_eur(*P1, 0, "call")
+    # parameter sets that would drive exp() out of its finite range (the reference prints inf / NaN there) are refused,
+    # not priced wrongly: sigma = 90 puts |x| up to 90*8.5 in play; so does a replayed "normal" of 1e6
+    for fn, extra in ((gpu.mc_eur, ()), (gpu.mc_asia, (1,)), (gpu.mc_amer, (1,))):
+        with pytest.raises(ValueError):
+            fn(100, 100, .05, 90.0, 1, 1000, *extra, "call")
+    with pytest.raises(ValueError):
+        gpu.mc_eur_multi(100, 100, .05, 90.0, 1, 1000, "call", 4, 0.5)
+    with pytest.raises(ValueError):
+        gpu.mc_eur(*P1, 4, "call", replay=np.array([0.1, 1e6, 0.0, float("nan")]))
+    assert gpu.mc_eur(100, 100, .05, 3.0, 1, 1000, "call", seed=1).price > 0      # large but representable: priced
+    # more GPUs than the box has: an error at init (reference src/mc_eur_mpi.cpp:58-62 fails loudly at MPI_Init), not a clamp
+    gpu.shutdown()
+    try:
+        with pytest.raises(ValueError):
+            gpu.init(1000)
+    finally:
+        gpu.init(1)
     # a path store that cannot fit (2e9 paths x 50 dates = 800 GB) is refused cleanly and the library stays usable
     with pytest.raises(Exception) as ei:
         gpu.mc_amer(*P1, 2_000_000_000, 50, "put")
