@@ -6,12 +6,15 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 # library has one instantiation per kernel family and reads no environment variable on a pricing call.
 TUNEFLAG  := $(if $(TUNING),-DPCF_TUNING,)
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off --compress-mode=size $(TUNEFLAG)
-LOGDIR    := build/ptxas
+LOGDIR    := build/ptxas$(if $(TUNING),_tuning,)
 CSRC      := parcompfin_b200/csrc
-SRCS      := $(CSRC)/pcf_api.cu $(CSRC)/mc_kernels.cu $(CSRC)/basket_kernels.cu $(CSRC)/amer_kernels.cu $(CSRC)/binom_kernels.cu $(CSRC)/tree_kernels.cu $(CSRC)/peaks.cu
-OBJS      := $(SRCS:.cu=.o) $(CSRC)/fastmath_tables.o
+NAMES     := pcf_api mc_kernels basket_kernels amer_kernels binom_kernels tree_kernels peaks
+# objects live under build/ (git-ignored); the TUNING=1 flavour has its own objects and its own library name, so both
+# can sit side by side (tools/tune_*.py load parcompfin_b200/libpcf_tuning.so through PCF_LIB)
+OBJDIR    := build/obj$(if $(TUNING),_tuning,)
+OBJS      := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(NAMES))) $(OBJDIR)/fastmath_tables.o
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/pcf.h
-LIB       := parcompfin_b200/libpcf.so
+LIB       := parcompfin_b200/libpcf$(if $(TUNING),_tuning,).so
 HOST      := parcompfin_b200/host
 BINS      := bin/mc_eur bin/mc_eur_multi bin/mc_asia bin/mc_amer bin/binom_embar bin/binom_vanilla_eur bin/binom_vanilla_amer
 
@@ -19,10 +22,11 @@ BINS      := bin/mc_eur bin/mc_eur_multi bin/mc_asia bin/mc_amer bin/binom_embar
 all: lib bins oracle
 
 lib: $(LIB)
-$(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
-	@mkdir -p $(LOGDIR)
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(LOGDIR) $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(LOGDIR)/$(notdir $(@:.o=.log)) || { cat $(LOGDIR)/$(notdir $(@:.o=.log)); exit 1; }
-$(CSRC)/fastmath_tables.o: $(CSRC)/fastmath_tables.cpp $(CSRC)/fastmath.cuh
+$(OBJDIR)/fastmath_tables.o: $(CSRC)/fastmath_tables.cpp $(CSRC)/fastmath.cuh
+	@mkdir -p $(OBJDIR)
 	$(HOSTCXX) -std=c++17 -O2 -fPIC -fvisibility=hidden -ffp-contract=off -c $< -o $@
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $(OBJS) -ldl -lpthread
@@ -36,7 +40,7 @@ oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -rf $(OBJS) $(LOGDIR) $(LIB) $(BINS)
+	rm -rf build/obj build/obj_tuning build/ptxas build/ptxas_tuning parcompfin_b200/libpcf.so parcompfin_b200/libpcf_tuning.so $(BINS)
 
 # ---- the reference's own target names (reference Makefile:14-16,34,68,100,131,159), so that its run-scripts and habits
 # keep working: `make init`, `make mc_eur_bin` (called by runscript_mc_eur.sh:25 after it rewrites include/comparison.h),

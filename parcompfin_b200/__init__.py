@@ -16,7 +16,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcf.so")
+# PCF_LIB: another build of the same library (the `make lib TUNING=1` flavour with the launch-shape knobs, tools/tune_*.py)
+LIB_PATH = os.environ.get("PCF_LIB") or os.path.join(_HERE, "libpcf.so")
 
 # status codes (include/pcf.h)
 PCF_OK, PCF_EINVAL_PAYOFF, PCF_EODD_N, PCF_ESINGULAR, PCF_EINVAL, PCF_ENOTPD = 0, 1, 2, 3, 4, 5

@@ -30,6 +30,7 @@
 #include "reduce.cuh"
 #include "rng.cuh"
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 namespace pcf {
@@ -237,19 +238,37 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded: a protocol error must end in a trapped kernel (an error code on the host), never in a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded by the nanosecond timer (3x the exchange timeout: a producer legitimately waits while its consumers sit in a
+// date barrier): a protocol error must end in a trapped kernel -- an error code on the host -- never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 0) {
   uint32_t done;
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!done && ++spins > (1u << 30)) __trap();
+    if (hint_ns) {
+      // suspend-time hint: the thread sleeps in hardware until the phase completes (or hint_ns pass) instead of spinning
+      // through issue slots (used by the producer lane, whose try_wait loop was 12 % of all executed instructions)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(parity)
+          : "memory");
+    }
+    if (!done && (++spins & 63u) == 0u) {
+      const unsigned long long now = xchg_now_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 3ull * kXchgTimeoutNs) __trap();
+    }
   } while (!done);
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar`; streamed data is marked evict-first in L2
@@ -466,100 +485,48 @@ struct SweepPArgs {
   double* out;          // final (sum, sumsq), job-wide: host-mapped
   int* err_flag;        // host-mapped status word
   unsigned long long seq0;  // the iteration of date m publishes exchange seq0 + (M - m)
+  unsigned long long* dbg;  // PCF_TUNING builds: cycle counters summed over CTAs (tools/tune_amer_persistent.py)
+  int keep_last;            // row m-1 is loaded with L2 evict_last instead of evict_normal (see the producer)
+  int knobs;                // PCF_TUNING A/B bits: 1 producer waits with a suspend hint, 2 consumers too, 4 no reversal,
+                            // 8 back-off in the date-barrier poll
 };
 
-// State a consumer thread carries across the dates of the persistent kernel.
+#ifdef PCF_TUNING
+#define PCF_DBG_CLOCK(var) const long long var = clock64()
+#define PCF_DBG_ADD(acc, expr) acc += (expr)
+#else
+#define PCF_DBG_CLOCK(var)
+#define PCF_DBG_ADD(acc, expr)
+#endif
+
 template <typename WT>
-struct SweepCarry {
-  typename WhenQuad<WT>::Vec wnext;  // dates of the first tile of the coming date (held in registers, never re-read)
-  uint32_t it;                       // ring iterations so far: slot = it % kStages, phase = (it / kStages) & 1
-};
+__host__ __device__ constexpr size_t sweep_stage_bytes() { return (size_t)kTilePaths * (8 + 8 + sizeof(WT)); }
 
-// One date of the persistent kernel, consumer side: all tiles of this CTA at date m.
-template <typename WT, bool kFinal, int kStages>
-__device__ __forceinline__ void consume_date(const SweepPArgs& a, const DateRule& R, int m, int nk, SweepCarry<WT>& cy,
-                                             unsigned char* ring, uint64_t* s_full, uint64_t* s_empty,
-                                             const double* s_disc, double2 (*s_wacc)[8]) {
-  typedef WhenQuad<WT> WQ;
-  typedef typename WQ::Vec WVec;
-  constexpr size_t kStage = (size_t)kTilePaths * 16;
-  const int tid = threadIdx.x;
-  const int M = a.M;
-  const bool first = (m == M);
-  const bool rev = ((M - m) & 1) != 0;
-  const long long Np = a.Np;
-  const double sgn = (double)a.cp, nE = -sgn * a.E;
-  const size_t row_bytes = (size_t)Np * 8;
-  WT* when = reinterpret_cast<WT*>(a.when);
-  // address of paths[d][n] for this thread's first path of tile 0 is colp0 + d*row_bytes (row d-1 holds date d)
-  const char* colp0 = reinterpret_cast<const char*>(a.paths) + (size_t)tid * 32 - row_bytes;
-  double run[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) run[k] = 0.0;
-  int cnt = 0;
-  for (int kk = 0; kk < nk; ++kk) {
-    const long long t = blockIdx.x + (long long)(rev ? nk - 1 - kk : kk) * gridDim.x;
-    const long long c0t = t * kTilePaths;
-    const bool live = c0t + 4 * tid < Np;  // Np is a multiple of 16: a quad is live or dead as a whole
-    WVec* wp = reinterpret_cast<WVec*>(when + c0t) + tid;
-    WVec wv = cy.wnext;
-    if (kk + 1 < nk && !first) {
-      // dates of the NEXT tile: this thread's own store of the previous date, fetched one tile ahead
-      const long long c0n = (blockIdx.x + (long long)(rev ? nk - 2 - kk : kk + 1) * gridDim.x) * kTilePaths;
-      if (c0n + 4 * tid < Np) cy.wnext = __ldcg(reinterpret_cast<const WVec*>(when + c0n) + tid);
-    }
-    const uint32_t slot = cy.it % kStages, ph = (cy.it / kStages) & 1u;
-    ++cy.it;
-    const unsigned char* st = ring + (size_t)slot * kStage;
-    mbar_wait(&s_full[slot], ph);
-    const double2 sa = *reinterpret_cast<const double2*>(st + tid * 32);
-    const double2 sb = *reinterpret_cast<const double2*>(st + tid * 32 + 16);
-    double2 pa = make_double2(0.0, 0.0), pb = pa;
-    if (!kFinal) {
-      pa = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32);
-      pb = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32 + 16);
-    }
-    // generic-proxy reads of the slot must be ordered before the TMA engine (async proxy) refills it
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&s_empty[slot]);
-    if (first) wv = WQ::splat(M);
-    if (!live) wv = WQ::splat(m);  // dead quad (tail of the last tile): date m, no flag, never in the money
-
-    const double src[4] = {sa.x, sa.y, sb.x, sb.y};
-    const double sp[4] = {pa.x, pa.y, pb.x, pb.y};
-    int w[4];
-    WQ::unpack(wv, w);
-    const char* colp = colp0 + (size_t)c0t * 8;
-    const bool changed = sweep_quad<WT, !kFinal, kFinal>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes, s_disc,
-                                                         s_disc + (M + 1), run, cnt);
-    const WVec wnew = WQ::pack(w);
-    if (first) {
-      if (live) *wp = wnew;                                           // mc_amer.cpp:23-27
-    } else if (R.mode >= 2) {
-      if (__any_sync(0xffffffffu, changed) && live) *wp = wnew;       // whole 128-byte lines back
-    } else if (changed) {
-      *wp = wnew;
-    }
-    if (kk + 1 == nk) cy.wnext = wnew;  // the coming date starts on this tile
-    if ((kk & (kMomFold - 1)) == kMomFold - 1) fold_runs<kFinal ? 2 : 8, !kFinal>(run, cnt, s_wacc, tid);
-  }
-  fold_runs<kFinal ? 2 : 8, !kFinal>(run, cnt, s_wacc, tid);
-}
-
+// The exercise dates of a tile reach the consumers through the ring like the rows do, which keeps the tile loop the one
+// of the per-date kernel (the first persistent build fetched them per thread -- a register prefetch that ptxas spilled
+// right after the load, then an asynchronous word copy -- and its tile loop swung between 22 and 30 ms from one build to
+// the next, profiles/r2_tune_amer_persistent.log). The dates of date m-1 are the consumers' own generic-proxy stores of
+// date m, read back by the TMA engine (async proxy): every consumer thread issues fence.proxy.async after its last store
+// of a date and its warp arrives on s_done; the producer issues the ROW copies of the first kStages tiles of the new date
+// as slots free up, waits for s_done, and only then issues their date copies (all later tiles of a date were written
+// before s_done completed, so they need no further care). Tiles are static per CTA (blockIdx.x + k * grid), so no other
+// CTA's stores are involved; the walk over them alternates direction from date to date, which makes the first tiles of
+// a date the ones whose rows were read last (L2) -- and exactly the ones the deferred copies cover.
 template <typename WT, int kStages>
 __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persistent_kernel(SweepPArgs a, PeerLink link) {
-  constexpr size_t kStage = (size_t)kTilePaths * 16;  // row m + row m-1; the dates travel through registers
+  typedef WhenQuad<WT> WQ;
+  typedef typename WQ::Vec WVec;
+  constexpr size_t kStage = sweep_stage_bytes<WT>();
   __shared__ double s_mom[kXchgVals];
   __shared__ double s_coef[3];
-  __shared__ double s_red[kSweepConsumers / 32][2];
   __shared__ double s_pub[kXchgVals + 8];
   __shared__ int s_mode, s_last;
-  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_done;
   __shared__ double2 s_wacc[kSweepConsumers / 32][8];  // per-WARP compensated totals of the current date
   extern __shared__ __align__(128) unsigned char dyn[];
   unsigned char* ring = dyn;                                                   // kStages x kStage
-  double* s_disc = reinterpret_cast<double*>(dyn + (size_t)kStages * kStage);  // exp(-r dt k), k = 0..M, then exp(-r k dt)
+  double* s_disc = reinterpret_cast<double*>(dyn + (size_t)kStages * kStage);  // exp(-r dt k), k = 0..M
+  double* s_abs = s_disc + (a.M + 1);                                          // exp(-r k dt)
   const int tid = threadIdx.x;
   const int M = a.M;
   for (int k = tid; k < 2 * (M + 1); k += blockDim.x) s_disc[k] = c_amer_tab[kDiscFwd + k];
@@ -568,6 +535,7 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persi
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], kSweepConsumers / 32);
     }
+    mbar_init(&s_done, kSweepConsumers / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -575,10 +543,8 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persi
 
   const long long Np = a.Np;
   const long long ntiles = (Np + kTilePaths - 1) / kTilePaths;
-  // tiles blockIdx.x, blockIdx.x + grid, ...: the SAME tiles at every date, so a path's exercise date is only ever
-  // touched by one thread of one CTA (no cross-thread visibility to arrange) and the first tile of date m-1 is the last
-  // tile of date m (the walk alternates its direction), whose dates are still in registers and whose rows are in L2
-  const int nk = (blockIdx.x < ntiles) ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  const int nk = (blockIdx.x < ntiles) ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;  // this CTA's tiles
+  WT* when = reinterpret_cast<WT*>(a.when);
 
   if (tid >= kSweepConsumers) {
     // ---- producer warp: one elected lane keeps the ring full, across date boundaries
@@ -587,23 +553,40 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persi
       // one ends, so it keeps the default policy
       uint64_t pol, pol_keep;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
-      uint32_t it = 0;
+      if (a.keep_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+      uint32_t it = 0, done_parity = 0;
       for (int m = M; m >= 1; --m) {
-        const bool rev = ((M - m) & 1) != 0;
+        const bool first = (m == M);
+        const bool rev = ((M - m) & 1) != 0 && !(a.knobs & 4);
         const double* row_m = a.paths + (size_t)(m - 1) * Np;
         const double* row_p = a.paths + (size_t)(m > 1 ? m - 2 : 0) * Np;
-        for (int kk = 0; kk < nk; ++kk, ++it) {
-          const long long t = blockIdx.x + (long long)(rev ? nk - 1 - kk : kk) * gridDim.x;
-          const uint32_t slot = it % kStages, ph = (it / kStages) & 1u;
-          mbar_wait(&s_empty[slot], ph ^ 1);
-          const long long c0 = t * kTilePaths;
+        const uint32_t per_path = (m > 1 ? 16u : 8u) + (first ? 0u : (uint32_t)sizeof(WT));
+        // tile kk of this date: waits for its slot, arms the barrier with the bytes of rows AND dates, copies the rows
+        // and -- unless deferred -- the dates
+        auto issue = [&](int kk, bool rows, bool dates) {
+          const long long c0 = (blockIdx.x + (long long)(rev ? nk - 1 - kk : kk) * gridDim.x) * kTilePaths;
           const uint32_t n = (uint32_t)((Np - c0 < kTilePaths) ? (Np - c0) : kTilePaths);  // multiple of 16
+          const uint32_t slot = (it + (uint32_t)kk) % kStages, ph = ((it + (uint32_t)kk) / kStages) & 1u;
           unsigned char* st = ring + (size_t)slot * kStage;
-          mbar_arrive_expect_tx(&s_full[slot], n * (m > 1 ? 16u : 8u));
-          bulk_g2s(st, row_m + c0, n * 8u, &s_full[slot], pol);
-          if (m > 1) bulk_g2s(st + kTilePaths * 8, row_p + c0, n * 8u, &s_full[slot], pol_keep);
+          if (rows) {
+            mbar_wait(&s_empty[slot], ph ^ 1, (a.knobs & 1) ? 2000u : 0u);
+            mbar_arrive_expect_tx(&s_full[slot], n * per_path);
+            bulk_g2s(st, row_m + c0, n * 8u, &s_full[slot], pol);
+            if (m > 1) bulk_g2s(st + kTilePaths * 8, row_p + c0, n * 8u, &s_full[slot], pol_keep);
+          }
+          if (dates) bulk_g2s(st + kTilePaths * 16, when + c0, n * (uint32_t)sizeof(WT), &s_full[slot], pol_keep);
+        };
+        const int nd = first ? 0 : (nk < kStages ? nk : kStages);
+        for (int kk = 0; kk < nd; ++kk) issue(kk, true, false);   // rows early: they do not depend on date m+1
+        if (nd > 0) {
+          mbar_wait(&s_done, done_parity, (a.knobs & 1) ? 2000u : 0u);  // this CTA's stores of date m+1 are complete
+          done_parity ^= 1u;
+          asm volatile("fence.proxy.async;" ::: "memory");
+          for (int kk = 0; kk < nd; ++kk) issue(kk, false, true);
         }
+        for (int kk = nd; kk < nk; ++kk) issue(kk, true, !first);
+        it += (uint32_t)nk;
       }
     }
     return;
@@ -611,29 +594,98 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persi
 
   // ---- consumers: thread `tid` owns paths 4 tid .. 4 tid + 3 of every tile (one 32-byte sector per row)
   const double sgn = (double)a.cp, nE = -sgn * a.E;
-  SweepCarry<WT> cy;
-  cy.wnext = WhenQuad<WT>::splat(M);  // mc_amer.cpp:23-27: when = M
-  cy.it = 0;
+  const size_t row_bytes = (size_t)Np * 8;
+  // address of paths[d][n] for this thread's first path of tile 0 is colp0 + d*row_bytes (row d-1 holds date d)
+  const char* colp0 = reinterpret_cast<const char*>(a.paths) + (size_t)tid * 32 - row_bytes;
+  int s = 0;
+  uint32_t ph = 0;
+#ifdef PCF_TUNING
+  long long dbg_wait = 0, dbg_tiles = 0, dbg_arrive = 0;
+  const long long dbg_t0 = clock64();
+#endif
 
   for (int m = M; m >= 1; --m) {
     const bool first = (m == M), final_date = (m == 1);
+    const bool rev = ((M - m) & 1) != 0 && !(a.knobs & 4);
     if ((tid & 31) == 0) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) s_wacc[tid >> 5][k] = make_double2(0.0, 0.0);
     }
+    PCF_DBG_CLOCK(dbg_a);
     if (!first) {
       // moments of date m: every rank's publication (this GPU's own included) in this GPU's mailbox
-      if (tid < 32) peer_gather_warp<kXchgVals>(link, a.seq0 + (unsigned long long)(M - m - 1), s_mom);
+      if (tid < 32)
+        peer_gather_warp<kXchgVals>(link, a.seq0 + (unsigned long long)(M - m - 1), s_mom, (a.knobs & 8) ? 500u : 0u);
       consumer_bar();
       if (tid == 0) solve_date(s_mom, a.lsm, &s_mode, s_coef, a.err_flag);
     } else if (tid == 0) {
       s_mode = 0;
     }
     consumer_bar();
+    PCF_DBG_CLOCK(dbg_b);
     const DateRule R = make_rule<WT>(s_mode, s_coef, sgn, nE, m);
-    if (final_date) consume_date<WT, true, kStages>(a, R, m, nk, cy, ring, s_full, s_empty, s_disc, s_wacc);
-    else consume_date<WT, false, kStages>(a, R, m, nk, cy, ring, s_full, s_empty, s_disc, s_wacc);
+    // the tile loop, instantiated twice (dates M..2: moments of date m-1; date 1: the final sum) so that each loop is
+    // allocated for its own body
+    auto tiles = [&](auto final_tag) {
+      constexpr bool kFin = decltype(final_tag)::value;
+      double run[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) run[k] = 0.0;
+      int cnt = 0, fold = 0;
+      long long c0t = (blockIdx.x + (long long)(rev ? nk - 1 : 0) * gridDim.x) * kTilePaths;
+      const long long cstep = (rev ? -(long long)gridDim.x : (long long)gridDim.x) * kTilePaths;
+      for (int kk = 0; kk < nk; ++kk, c0t += cstep) {
+        const unsigned char* st = ring + (size_t)s * kStage;
+        const bool live = c0t + 4 * tid < Np;  // Np is a multiple of 16: a quad is live or dead as a whole
+        mbar_wait(&s_full[s], ph, (a.knobs & 2) ? 2000u : 0u);
+        const double2 sa = *reinterpret_cast<const double2*>(st + tid * 32);
+        const double2 sb = *reinterpret_cast<const double2*>(st + tid * 32 + 16);
+        double2 pa = make_double2(0.0, 0.0), pb = pa;
+        if (!kFin) {
+          pa = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32);
+          pb = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32 + 16);
+        }
+        WVec wv = *reinterpret_cast<const WVec*>(st + kTilePaths * 16 + tid * sizeof(WVec));
+        // generic-proxy reads of the slot must be ordered before the TMA engine (async proxy) refills it: without
+        // this fence a deep ring at 2 CTAs/SM produced stale reads (observed as run-to-run price noise)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
+        if (++s == kStages) { s = 0; ph ^= 1; }
+        if (first) wv = WQ::splat(M);  // mc_amer.cpp:23-27 (the slot's date area was not filled)
+        if (!live) wv = WQ::splat(m);  // dead quad (tail of the last tile): date m, no flag, never in the money
+
+        const double src[4] = {sa.x, sa.y, sb.x, sb.y};
+        const double sp[4] = {pa.x, pa.y, pb.x, pb.y};
+        int w[4];
+        WQ::unpack(wv, w);
+        WVec* wp = reinterpret_cast<WVec*>(when + c0t) + tid;
+        const char* colp = colp0 + (size_t)c0t * 8;
+        const bool changed = sweep_quad<WT, !kFin, kFin>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes, s_disc, s_abs, run, cnt);
+        if (first) {
+          if (live) *wp = WQ::pack(w);                                          // initialise the state
+        } else if (R.mode >= 2) {
+          if (__any_sync(0xffffffffu, changed) && live) *wp = WQ::pack(w);      // whole 128-byte lines back
+        } else if (changed) {
+          *wp = WQ::pack(w);
+        }
+        if (++fold == kMomFold) {
+          fold_runs<kFin ? 2 : 8, !kFin>(run, cnt, s_wacc, tid);
+          fold = 0;
+        }
+      }
+      fold_runs<kFin ? 2 : 8, !kFin>(run, cnt, s_wacc, tid);
+    };
+    if (final_date) tiles(std::true_type{});
+    else tiles(std::false_type{});
+    // this date's stores of exercise dates are complete: order them before the TMA engine's reads of the next date
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&s_done);
     consumer_bar();
+    PCF_DBG_CLOCK(dbg_c);
+    PCF_DBG_ADD(dbg_wait, dbg_b - dbg_a);
+    PCF_DBG_ADD(dbg_tiles, dbg_c - dbg_b);
 
     // ---- split grid barrier, arrival: CTA totals (one lane per moment, warps merged in order) -> global partials
     if (tid < 32) {
@@ -658,23 +710,27 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persi
       // ---- the last CTA to arrive folds all partials in block order and publishes (reduce.cuh grid_reduce, restated
       // for the 8 consumer warps: the producer warp is busy refilling the ring and takes no part in barriers)
       __threadfence();
-      for (int k = 0; k < 8; ++k) {
+      {
+        // warp k folds moment k over all CTAs: lanes stride the blocks, then a fixed shuffle tree. The loads are issued
+        // as one batch (L2, independent) before the dependent chain of compensated adds
+        const int k = tid >> 5;
+        constexpr int kBatch = 8;
         Comp acc;
-        for (unsigned int b = tid; b < gridDim.x; b += kSweepConsumers) {
-          const volatile double* pp = a.partials + ((size_t)b * 8 + k) * 2;
-          acc.merge(Comp(pp[0], pp[1]));
+        for (unsigned int b0 = tid & 31; b0 < gridDim.x; b0 += 32 * kBatch) {
+          double2 v[kBatch];
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j) {
+            const unsigned int b = b0 + 32 * j;
+            v[j] = (b < gridDim.x) ? __ldcg(reinterpret_cast<const double2*>(a.partials + ((size_t)b * 8 + k) * 2))
+                                   : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j) acc.merge(Comp(v[j].x, v[j].y));
         }
         acc = warp_reduce(acc);
-        if ((tid & 31) == 0) { s_red[tid >> 5][0] = acc.hi; s_red[tid >> 5][1] = acc.lo; }
-        consumer_bar();
-        if (tid == 0) {
-          Comp tot;
-#pragma unroll
-          for (int wq = 0; wq < kSweepConsumers / 32; ++wq) tot.merge(Comp(s_red[wq][0], s_red[wq][1]));
-          s_pub[k] = tot.value();
-        }
-        consumer_bar();
+        if ((tid & 31) == 0) s_pub[k] = acc.value();
       }
+      consumer_bar();
       if (tid == 0) *a.ticket = 0u;
       const unsigned long long seq_out = a.seq0 + (unsigned long long)(M - m);
       peer_publish<kXchgVals>(link, seq_out, s_pub, consumer_bar);
@@ -685,7 +741,21 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persi
         if (tid < 2) a.out[tid] = s_pub[8 + tid];
       }
     }
+    PCF_DBG_ADD(dbg_arrive, clock64() - dbg_c);
   }
+#ifdef PCF_TUNING
+  if (tid == 0 && a.dbg) {  // sums and maxima over CTAs, in cycles: date-barrier wait, tile loops, arrival/fold, total
+    const long long tot = clock64() - dbg_t0;
+    atomicAdd(a.dbg + 0, (unsigned long long)dbg_wait);
+    atomicAdd(a.dbg + 1, (unsigned long long)dbg_tiles);
+    atomicAdd(a.dbg + 2, (unsigned long long)dbg_arrive);
+    atomicAdd(a.dbg + 3, (unsigned long long)tot);
+    atomicMax(a.dbg + 4, (unsigned long long)dbg_wait);
+    atomicMax(a.dbg + 5, (unsigned long long)dbg_tiles);
+    atomicMax(a.dbg + 6, (unsigned long long)tot);
+    atomicAdd(a.dbg + 7, 1ull);
+  }
+#endif
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -707,9 +777,6 @@ struct SweepArgs {
   double* out;          // kMoments: the 8 moments of date m-1; kFinal: sum, sumsq
   int* err_flag;
 };
-
-template <typename WT>
-__host__ __device__ constexpr size_t sweep_stage_bytes() { return (size_t)kTilePaths * (8 + 8 + sizeof(WT)); }
 
 template <typename WT, bool kMoments, bool kFinal>
 __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_kernel(SweepArgs a, PeerLink link_out) {
@@ -872,7 +939,7 @@ static int launch_sweep(Ctx& c, bool final_date, int grid, int stages, const Swe
 template <typename WT, int kStages>
 static int launch_sweep_persistent(Ctx& c, const SweepPArgs& a, const PeerLink& link, long long ntiles) {
   auto k = amer_sweep_persistent_kernel<WT, kStages>;
-  const size_t dsm = (size_t)kStages * kTilePaths * 16 + 2 * sizeof(double) * (a.M + 1);
+  const size_t dsm = (size_t)kStages * sweep_stage_bytes<WT>() + 2 * sizeof(double) * (a.M + 1);
   PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
   int per_sm = 0;
   PCF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kSweepBlock, dsm));
@@ -886,6 +953,10 @@ static int launch_sweep_persistent(Ctx& c, const SweepPArgs& a, const PeerLink& 
   SweepPArgs args = a;
   PeerLink l = link;
   void* params[] = {(void*)&args, (void*)&l};
+  if (tuning_env("PCF_AMER_NOCOOP")) {  // A/B: plain launch (the grid fits the device, so every CTA is resident anyway)
+    k<<<dim3((unsigned)grid), dim3(kSweepBlock), dsm, c.stream>>>(args, l);
+    return PCF_OK;
+  }
   PCF_CUDA(cudaLaunchCooperativeKernel((const void*)k, dim3((unsigned)grid), dim3(kSweepBlock), params, dsm, c.stream));
   return PCF_OK;
 }
@@ -972,7 +1043,9 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   const bool w8 = amer_when_bytes(M) == 1;
   const bool nccl_path = c.world > 1 && !use_peer(c);
   const bool chain = nccl_path || tuning_env("PCF_AMER_CHAIN") != nullptr;
-  int stages = 2;
+  // ring depth 2 for both drivers: a third stage measured slower in the per-date chain
+  // (profiles/r1l_tune_amer_sweep_variants.log) and the same in the persistent kernel (profiles/r2_tune_amer_persistent.log)
+  int stages = 0;
   if (const char* v = tuning_env("PCF_AMER_SWEEP")) stages = std::max(2, std::min(kMaxStages, atoi(v)));
   if (!chain) {
     // ONE cooperative launch; moments travel through the mailboxes (this GPU's own when it is alone)
@@ -980,6 +1053,13 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
     sp.paths = paths; sp.when = when; sp.Np = Np; sp.E = p.E; sp.cp = p.cp; sp.M = M;
     sp.lsm = (p.flags & PCF_FLAG_AMER_LSM) ? 1 : 0;
     sp.partials = c.d_partials; sp.ticket = c.d_ticket; sp.out = c.res_dev; sp.err_flag = c.flag_dev;
+    sp.dbg = nullptr;
+    sp.keep_last = tuning_env("PCF_AMER_L2") ? atoi(tuning_env("PCF_AMER_L2")) : 0;
+    sp.knobs = tuning_env("PCF_AMER_KNOBS") ? atoi(tuning_env("PCF_AMER_KNOBS")) : 1;
+#ifdef PCF_TUNING
+    sp.dbg = reinterpret_cast<unsigned long long*>(c.d_out + 24);  // read back with pcf_debug_counters()
+    PCF_CUDA(cudaMemsetAsync(sp.dbg, 0, 8 * sizeof(unsigned long long), c.stream));
+#endif
     sp.seq0 = c.xchg_seq + 1;
     c.xchg_seq += (unsigned long long)M;  // M exchanges, whether or not other ranks exist
     PeerLink l = c.link;
@@ -993,6 +1073,9 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
     if (stages == 3) {
       if (w8) PCF_TRY((launch_sweep_persistent<uint8_t, 3>(c, sp, l, ntiles)));
       else PCF_TRY((launch_sweep_persistent<uint16_t, 3>(c, sp, l, ntiles)));
+    } else if (stages == 4) {
+      if (w8) PCF_TRY((launch_sweep_persistent<uint8_t, 4>(c, sp, l, ntiles)));
+      else PCF_TRY((launch_sweep_persistent<uint16_t, 4>(c, sp, l, ntiles)));
     } else
 #endif
     if (w8) PCF_TRY((launch_sweep_persistent<uint8_t, 2>(c, sp, l, ntiles)));
@@ -1013,7 +1096,7 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   SweepArgs sa;
   sa.paths = paths; sa.when = when; sa.Np = Np; sa.E = p.E; sa.cp = p.cp; sa.M = M;
   sa.lsm = (p.flags & PCF_FLAG_AMER_LSM) ? 1 : 0;
-  sa.stages = stages;
+  sa.stages = stages ? stages : 2;
   sa.partials = c.d_partials; sa.ticket = c.d_ticket; sa.err_flag = c.flag_dev;
   double* mom[2] = {c.d_out + 8, c.d_out + 16};
   PeerLink none = c.link;
@@ -1026,8 +1109,8 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
     sa.mom_in = mom[m & 1];
     if (m < M) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));
     sa.out = (m > 1) ? mom[(m - 1) & 1] : final_out(c);
-    if (w8) PCF_TRY(launch_sweep<uint8_t>(c, m == 1, grid, stages, sa, none));
-    else PCF_TRY(launch_sweep<uint16_t>(c, m == 1, grid, stages, sa, none));
+    if (w8) PCF_TRY(launch_sweep<uint8_t>(c, m == 1, grid, sa.stages, sa, none));
+    else PCF_TRY(launch_sweep<uint16_t>(c, m == 1, grid, sa.stages, sa, none));
     c.launches++;
   }
   PCF_CUDA(cudaGetLastError());

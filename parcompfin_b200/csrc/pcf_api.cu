@@ -899,6 +899,17 @@ int pcf_philox4x32_10(const unsigned int ctr[4], const unsigned int key[2], unsi
   return PCF_OK;
 }
 
+#ifdef PCF_TUNING
+// Tuning builds only (not declared in include/pcf.h): the 8 cycle counters the persistent sweep kernel leaves behind.
+__attribute__((visibility("default"))) int pcf_debug_counters(unsigned long long out[8]) {
+  if (g_ctx.empty()) return PCF_ENOINIT;
+  Ctx& c = g_ctx[0];
+  PCF_CUDA(cudaSetDevice(c.device));
+  PCF_CUDA(cudaMemcpy(out, c.d_out + 24, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return PCF_OK;
+}
+#endif
+
 int pcf_fp64_peak(double seconds_target, double* dfma_per_sec) {
   if (g_ctx.empty()) return PCF_ENOINIT;
   PCF_CUDA(cudaSetDevice(g_ctx[0].device));

@@ -57,12 +57,14 @@ __device__ __forceinline__ bool xchg_poisoned(const PeerLink& L, unsigned long l
 }
 
 // Spins until *f == seq. Returns false on timeout or poison (and records it).
-__device__ __forceinline__ bool xchg_wait_flag(const PeerLink& L, unsigned long long seq, volatile unsigned long long* f) {
+__device__ __forceinline__ bool xchg_wait_flag(const PeerLink& L, unsigned long long seq, volatile unsigned long long* f,
+                                               unsigned int backoff_ns = 0) {
   if (*f == seq) return true;
   Mailbox* me = L.peer[L.rank];
   const unsigned long long t0 = xchg_now_ns();
   unsigned int spins = 0;
   while (*f != seq) {
+    if (backoff_ns) __nanosleep(backoff_ns);
     if ((++spins & 255u) == 1u) {
       const bool late = xchg_now_ns() - t0 > kXchgTimeoutNs;
       if (late || xchg_poisoned(L, seq)) {
@@ -90,10 +92,11 @@ __device__ __forceinline__ void peer_publish(const PeerLink& L, unsigned long lo
     const int r = t / K, k = t - r * K;
     volatile double* dst = &L.peer[r]->vals[slot][L.rank][k];
     *dst = vals[k];
-    __threadfence_system();
   }
   sync();
   if (t < L.world) {
+    // release: the barrier orders every thread's value stores before this fence, and fences are cumulative, so one
+    // system-scope fence in the flag writer covers them all
     __threadfence_system();
     volatile unsigned long long* f = &L.peer[t]->flags[slot][L.rank];
     *f = seq;
@@ -107,14 +110,15 @@ __device__ __forceinline__ void peer_publish(const PeerLink& L, const double* va
 // One warp (lanes 0..31 of the caller) waits for every rank's publication and adds the K values in rank order into
 // out[0..K) (shared or global memory). Failure -> NaN. Ends with __syncwarp().
 template <int K>
-__device__ __forceinline__ void peer_gather_warp(const PeerLink& L, unsigned long long seq, double* out) {
+__device__ __forceinline__ void peer_gather_warp(const PeerLink& L, unsigned long long seq, double* out,
+                                                 unsigned int backoff_ns = 0) {
   static_assert(K <= 32, "one lane per value");
   const int slot = (int)(seq & 1ull);
   Mailbox* me = L.peer[L.rank];
   const int t = threadIdx.x & 31;
   bool ok = true;
   if (t < L.world) {
-    ok = xchg_wait_flag(L, seq, &me->flags[slot][t]);
+    ok = xchg_wait_flag(L, seq, &me->flags[slot][t], backoff_ns);
     __threadfence_system();
   }
   ok = __all_sync(0xffffffffu, ok);
