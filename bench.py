@@ -16,7 +16,13 @@ split over the N GPUs by path index -- strong scaling, Philox keyed by global pa
           has no FP64 figure)
   cpu_baseline  the reference's own OpenMP program (oracle/_ref/mc_asia_omp, compiled from the unmodified
           sources) on this box's host cores, bounded sample
-  others  the other four BASELINE.json configs, one short measurement each, same definitions
+  others  the other four BASELINE.json configs, one short measurement each, same definitions; configs 1 and 2 also at
+          their STATED sizes (1e7 paths; N = 1e5, 1e6, 1e7), which are launch-latency bound: microseconds per call on the
+          device clock and on the C-ABI call's own wall clock, next to the floor (a one-unit call of the same method)
+  parity  (N > 1 only, outside the timed region) every method priced at a small size by the N ranks together -- with the
+          NVLink peer mailboxes and again with ncclAllReduce -- against rank 0 alone on one GPU: relative differences and
+          an overall `ok` (bound 1e-13; identical normal streams, only the summation order differs). The reference's own
+          distributed check is `mpirun -n 4` in its *_tst targets (reference Makefile:45-46,79-80).
 
 `--impl reference` times the reference's CPU implementation (rank 0 only) on a bounded sample per step.
 """
@@ -44,12 +50,12 @@ WORKLOADS = {
     "mc_asia": dict(config="mc_asia call 100/100/.05/.2/1, 1e9 paths x 252 dates (BASELINE config 3)",
                     N=1_000_000_000, M=252, steps_per_unit=252, slots=55.0, bound="fp64", unit="path-steps/s",
                     kernel="mc_asia_kernel", exec_cycles=97.0,
-                    exec_src="SASS of the shipped loop (tests/sass_count.py): 31.5 FP64 + 8.5 IMAD.WIDE per path-step"),
+                    exec_src="SASS of the shipped loop (tools/sass_count.py): 31.5 FP64 + 8.5 IMAD.WIDE per path-step"),
     "mc_eur": dict(config="mc_eur call 100/100/.05/.2/1, 2e9 paths (config 1 at the size SURVEY 8d quotes the "
                           "roofline on; 1e7 paths is 30 us of work)",
                    N=2_000_000_000, M=0, steps_per_unit=1, slots=60.0, bound="fp64", unit="path-steps/s",
                    kernel="mc_eur_kernel", exec_cycles=106.75,
-                   exec_src="SASS of the shipped loop (tests/sass_count.py): 34.4 FP64 + 9.5 IMAD.WIDE per path"),
+                   exec_src="SASS of the shipped loop (tools/sass_count.py): 34.4 FP64 + 9.5 IMAD.WIDE per path"),
     "mc_eur_multi": dict(config="mc_eur_multi call, d=16 rho=0.5, 1e9 paths (BASELINE config 4)",
                          N=1_000_000_000, M=0, steps_per_unit=1, slots=990.0, bound="fp64", unit="path-steps/s",
                          kernel="mc_basket_equi_kernel", assets=16, rho=0.5),
@@ -61,7 +67,7 @@ WORKLOADS = {
                               exec_src="ncu: 640 FP64 + 160 IMAD.WIDE warp instructions per path"),
     "mc_amer": dict(config="mc_amer put, 1e8 paths x 50 exercise dates, paths in HBM (BASELINE config 5)",
                     N=100_000_000, M=50, steps_per_unit=50, bytes=36.0, bound="hbm", unit="path-steps/s",
-                    kernel="amer_sweep_kernel+amer_paths_kernel"),
+                    kernel="amer_sweep_persistent_kernel+amer_paths_kernel+amer_pad_kernel", traffic_all=True),
     "binom_embar": dict(config="binom_embar call 100/100/.05/.2/1, N=1e8 steps (BASELINE config 2)",
                         N=100_000_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
                         kernel="binom_terms_kernel"),
@@ -75,6 +81,21 @@ WORKLOADS = {
                                    "quotes the binomial roofline at this size)",
                             N=2_147_483_647, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
                             kernel="binom_terms_kernel"),
+    # BASELINE configs 1 and 2 AS STATED (reference src/mc_eur.cpp:23-25 at N = 1e7, src/binom_embar.cpp:34-46 at N = 1e5..1e7):
+    # tens of microseconds of work, bound by launch + completion latency (SURVEY 7 "Tiny workloads"); reported as
+    # microseconds per call with the floor beside them, the roofline figures stay on the large variants above
+    "mc_eur_stated": dict(config="mc_eur call 100/100/.05/.2/1, 1e7 paths (BASELINE config 1 as stated)",
+                          N=10_000_000, M=0, steps_per_unit=1, slots=60.0, bound="fp64", unit="path-steps/s",
+                          kernel="mc_eur_kernel", latency=True, method="mc_eur"),
+    "binom_embar_1e5": dict(config="binom_embar call 100/100/.05/.2/1, N=1e5 steps (BASELINE config 2, smallest stated size)",
+                            N=100_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
+                            kernel="binom_terms_kernel", latency=True, method="binom_embar"),
+    "binom_embar_1e6": dict(config="binom_embar call 100/100/.05/.2/1, N=1e6 steps (BASELINE config 2)",
+                            N=1_000_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
+                            kernel="binom_terms_kernel", latency=True, method="binom_embar"),
+    "binom_embar_1e7": dict(config="binom_embar call 100/100/.05/.2/1, N=1e7 steps (BASELINE config 2)",
+                            N=10_000_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
+                            kernel="binom_terms_kernel", latency=True, method="binom_embar"),
     # SURVEY 8(f).1 (widening row): algorithmic work = the recurrence as the reference writes it with tabulated powers:
     # 2 mul + add + IEEE division (10 slots, libdevice) [+ 2 mul, payoff 2, max 1 for the American tree]
     "binom_vanilla_amer": dict(config="binom_vanilla_amer put 100/100/.05/.2/1, N=1e5 layers (SURVEY 8f.1; the reference "
@@ -91,7 +112,7 @@ def run_ours_once(pcf, name, seed, N=None):
     a = (P["S0"], P["E"], P["r"], P["sigma"], P["T"])
     if name == "mc_asia":
         return pcf.mc_asia(*a, N, w["M"], "call", seed=seed)
-    if name == "mc_eur":
+    if name in ("mc_eur", "mc_eur_stated"):
         return pcf.mc_eur(*a, N, "call", seed=seed)
     if name == "mc_eur_multi":
         return pcf.mc_eur_multi(*a, N, "call", w["assets"], w["rho"], seed=seed)
@@ -105,9 +126,7 @@ def run_ours_once(pcf, name, seed, N=None):
                              weights=rng.dirichlet(np.ones(d)), cov=cov, seed=seed)
     if name == "mc_amer":
         return pcf.mc_amer(*a, N, w["M"], "put", seed=seed)
-    if name == "binom_embar":
-        return pcf.binom(*a, N, "call")
-    if name == "binom_embar_max":
+    if name in ("binom_embar", "binom_embar_max", "binom_embar_1e5", "binom_embar_1e6", "binom_embar_1e7"):
         return pcf.binom(*a, N, "call")
     if name == "binom_embar_noscreen":
         return pcf.binom(*a, N, "call", screen=False)
@@ -194,12 +213,23 @@ def cpu_reference_other(name, threads):
     try:
         if name == "mc_eur_multi":
             n = 2_000_000
+            if oracle.have_ref() and os.path.exists(os.path.join(oracle.REF_DIR, "mc_eur_multi_omp")):
+                sec = float(oracle.ref_row("mc_eur_multi_omp", "call", *a, n, 16, 0.5, threads)[12])
+                return {"value": n / sec, "unit": "path-steps/s", "cores": threads, "kind": "reference",
+                        "sample": f"{n} of 1e9 paths, d=16, {sec:.1f} s, mc_eur_multi_omp (unmodified reference source at "
+                                  "-O2, compiled against the stand-in Eigen/Boost headers of oracle/shim; its sample "
+                                  "generation is serial, src/mc_eur_multi_omp.cpp:31)"}
             _, sec = oracle.mc_basket_omp_timed(*a, n, "call", 16, 0.5, SEED0, threads)
             return {"value": n / sec, "unit": "path-steps/s", "cores": threads, "kind": "port",
                     "sample": f"{n} of 1e9 paths, d=16, {sec:.1f} s, oracle restatement with the OpenMP placement of "
                               "src/mc_eur_multi_omp.cpp:31-46 (serial sample generation)"}
         if not oracle.have_ref():
             return None
+        if name == "mc_eur_stated":
+            n = 10_000_000
+            sec = float(oracle.ref_row("mc_eur_omp", "call", *a, n, threads)[12])
+            return {"value": n / sec, "unit": "path-steps/s", "cores": threads, "kind": "reference",
+                    "sample": f"the full 1e7 paths, {sec * 1e3:.1f} ms, mc_eur_omp (unmodified reference source, -O2)"}
         if name == "mc_eur":
             n = 400_000_000
             sec = float(oracle.ref_row("mc_eur_omp", "call", *a, n, threads)[12])
@@ -210,7 +240,8 @@ def cpu_reference_other(name, threads):
             sec = float(oracle.ref_row("mc_amer_omp", "put", *a, n, M, threads)[12])
             return {"value": n * M / sec, "unit": "path-steps/s", "cores": threads, "kind": "reference",
                     "sample": f"{n} of 1e8 paths x {M} dates, {sec:.1f} s, mc_amer_omp (unmodified reference source, -O2)"}
-        if name in ("binom_embar", "binom_embar_noscreen", "binom_embar_max"):
+        if name in ("binom_embar", "binom_embar_noscreen", "binom_embar_max", "binom_embar_1e5", "binom_embar_1e6",
+                    "binom_embar_1e7"):
             n = 50_000
             sec = float(oracle.ref_row("binom_embar_omp", "call", *a, n, threads)[12])
             return {"value": (n + 1) / sec, "unit": "terms/s", "cores": threads, "kind": "reference",
@@ -264,26 +295,83 @@ def measure(pcf, dist, job, name, steps, warmup, N=None):
         torch.cuda.synchronize()
     dist.barrier(job)
     t0 = time.perf_counter()
-    dev, launches, last = [], 0, None
+    dev, launches, last, abi = [], 0, None, 0.0
     for i in range(steps):
         last = run_ours_once(pcf, name, SEED0 + i, N)   # synchronous: returns after the result is on the host
         dev.append(last.seconds_kernel)
+        abi += last.seconds_total
         launches += last.launches
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     dist.barrier(job)
     wall = time.perf_counter() - t0
     # max over ranks, per step for the device clock and once for the wall clock
-    red = dist.reduce_scalars(job, dev + [wall], "max")
+    red = dist.reduce_scalars(job, dev + [wall, abi], "max")
     tot_launch = dist.reduce_scalars(job, [float(launches)], "sum")[0]
-    return dict(device_s=sum(red[:-1]), wall_s=red[-1], launches=int(tot_launch), units=last.units,
+    return dict(device_s=sum(red[:-2]), wall_s=red[-2], abi_s=red[-1], launches=int(tot_launch), units=last.units,
                 price=last.price, se=last.std_error, t0=t0)
 
 
-def ncu_traffic(kernel_names):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu launch list of this very command
-    (profiles/ncu_traffic.json, written by tools/summarize_launches.py); None when no capture is committed. For a
-    workload made of several kernels the figure is per launch of the DOMINANT one (most DRAM bytes)."""
+PARITY_CASES = (
+    # (label, method, args, kwargs) -- small sizes of every method; N not divisible by the rank count; both mc_amer rules
+    ("mc_asia", "mc_asia", (100, 100, .05, .2, 1, 1_000_001, 252, "call"), {"seed": 31}),
+    ("mc_eur", "mc_eur", (100, 100, .05, .2, 1, 3_000_001, "put"), {"seed": 31}),
+    ("mc_eur_multi", "mc_eur_multi", (100, 100, .05, .2, 1, 500_001, "call", 16, 0.5), {"seed": 31}),
+    ("mc_eur_multi_eigen", "mc_eur_multi", (100, 100, .05, .2, 1, 200_001, "call", 4, 1.0), {"seed": 31}),
+    ("mc_amer_put", "mc_amer", (100, 100, .05, .2, 1, 1_000_002, 50, "put"), {"seed": 31}),
+    ("mc_amer_call", "mc_amer", (100, 110, .02, .75, 1, 200_000, 20, "call"), {"seed": 31}),
+    ("mc_amer_lsm", "mc_amer", (100, 100, .05, .2, 1, 400_000, 50, "put"), {"seed": 31, "lsm": True}),
+    ("mc_amer_tiny", "mc_amer", (100, 100, .05, .2, 1, 2, 5, "put"), {"seed": 31}),   # fewer pairs than ranks
+    ("binom_embar", "binom", (100, 100, .05, .2, 1, 1_000_001, "call"), {}),
+)
+PARITY_TOL = 1e-13
+
+
+def multi_gpu_parity(pcf, dist, job):
+    """Every method at a small size: rank 0 alone on one GPU, then the N ranks together with the NVLink peer mailboxes and
+    again with ncclAllReduce. Same Philox streams (keyed by global index), so only the summation order differs: relative
+    differences must stay below 1e-13. Runs outside the timed region; returns the dict for the JSON line (rank 0)."""
+    def price_all():
+        return {lab: getattr(pcf, meth)(*a, **kw).price for lab, meth, a, kw in PARITY_CASES}
+
+    single = None
+    if job.rank == 0:
+        pcf.init_rank(0, 1, job.local_rank, None)
+        single = price_all()
+        pcf.shutdown()
+    dist.barrier(job)
+    dist.init_library(job)
+    out = {"tolerance": PARITY_TOL, "ranks": job.world, "modes": {}}
+    modes = [("peer_mailbox", True)] if pcf.peer_active() else []
+    modes.append(("nccl_allreduce", False))
+    ok = True
+    for mode, peer in modes:
+        try:
+            pcf.peer_enable(peer)
+            multi = price_all()
+            if job.rank == 0:
+                errs = {lab: abs(multi[lab] - single[lab]) / max(abs(single[lab]), 1e-300) if single[lab] != 0
+                        else abs(multi[lab]) for lab in multi}
+                out["modes"][mode] = errs
+                ok = ok and all(e <= PARITY_TOL for e in errs.values())
+        except Exception as ex:  # a failure here must show up in the line, not kill the bench
+            out["modes"][mode] = {"error": str(ex)}
+            ok = False
+        dist.barrier(job)
+    if len(modes) == 2:
+        pcf.peer_enable(True)   # the timed region runs in the default mode
+    out["ok"] = bool(ok)
+    if job.rank == 0:
+        out["single_gpu_prices"] = single
+    return out
+
+
+def ncu_traffic(kernel_names, all_kernels=False):
+    """dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu launch list of this very command
+    (profiles/ncu_traffic.json, written by tools/summarize_launches.py); None when no capture is committed.
+    Default: bytes per launch of the DOMINANT kernel among `kernel_names` (most DRAM bytes). all_kernels=True: bytes per
+    STEP summed over every listed kernel (launches of a kernel per step = its launches / the dominant kernel's launches
+    in the capture) -- what a workload made of several kernels really moves."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(path):
         return None
@@ -291,13 +379,31 @@ def ncu_traffic(kernel_names):
         ks = json.load(open(path))["kernels"]
     except (ValueError, KeyError):
         return None
-    best = None
+    hits = []
     for frag in kernel_names.split("+"):
         for k, v in ks.items():
             if k.startswith(frag):
-                if best is None or v["dram_bytes_per_launch"] > best:
-                    best = v["dram_bytes_per_launch"]
-    return best
+                hits.append(v)
+    if not hits:
+        return None
+    dom = max(hits, key=lambda v: v["dram_bytes_per_launch"])
+    if not all_kernels:
+        return dom["dram_bytes_per_launch"]
+    steps = max(min(v["launches"] for v in hits if v["dram_bytes_per_launch"] > 0.25 * dom["dram_bytes_per_launch"]), 1)
+    return sum(v["dram_bytes_per_launch"] * v["launches"] for v in hits) / steps
+
+
+def binom_executed_slots(N):
+    """FP64 instructions per term the binomial kernel EXECUTES with its screening pass on: every pair costs
+    the two-logarithm screen (32), and only pairs with a term whose log-weight is above the -712 underflow rule go on to the
+    full saddle-point routine (150 more). Live pairs from the Gaussian envelope of the weights around N p."""
+    import math
+    _, _, p, q = __import__("oracle").binom_params(P["r"], P["sigma"], P["T"], N)
+    npq = N * p * q
+    half_width = math.sqrt(2.0 * npq * max(712.0 - 0.5 * math.log(2 * math.pi * npq), 1.0))
+    pairs = (N + 1) // 2
+    live = min(pairs, half_width + abs(N * p - N / 2.0) + 1)
+    return (32.0 * pairs + 150.0 * live) / (N + 1), live / pairs
 
 
 def roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src):
@@ -309,9 +415,32 @@ def roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src):
         # warp, IMAD.WIDE (Philox) 4 on the same pipe (tests/ubench); the pipe offers 2 x dfma_peak / 32 cycles per second.
         r["executed_pipe_frac"] = units_per_s * w["exec_cycles"] / (2.0 * fp64_dfma_per_s)
         r["executed_work"] = f"{w['exec_cycles']:g} FP64-pipe cycles per warp and unit ({w['exec_src']})"
-    r["traffic"] = ncu_traffic(w["kernel"])
+    if name.startswith("binom_embar") and name != "binom_embar_noscreen":
+        # the screening pass settles most pairs with ~32 FP64 instructions, so the ALGORITHMIC 85 slots per term (which the
+        # unscreened entry is quoted on) overstate what this run executed: report the rate against executed work and mark
+        # the algorithmic fraction as not creditable (shortcuts do not change the per-unit figure)
+        try:
+            slots, live = binom_executed_slots(WORKLOADS[name]["N"])
+            r["executed_frac"] = units_per_s * slots / fp64_dfma_per_s
+            r["executed_work"] = (f"{slots:.1f} FP64 instructions per term: 32 per pair for the screen + 150 more for the "
+                                  f"{100 * live:.2f} % of pairs that reach the full routine (DESIGN 4.4)")
+            r["frac_note"] = ("`frac` counts the algorithmic 85 slots for every term although the screen settles most of "
+                              "them early; the creditable figures are `executed_frac` here and `frac` of the screening-OFF "
+                              "entry")
+        except Exception as ex:  # the oracle's lattice helper is missing: leave the algorithmic figure alone
+            r["executed_work"] = f"unavailable ({ex})"
+    r["traffic"] = ncu_traffic(w["kernel"], w.get("traffic_all", False))
     if r["traffic"] is not None:
-        r["traffic_source"] = "profiles/ncu_traffic.json: DRAM read+write bytes per launch of the dominant kernel (ncu)"
+        if w.get("traffic_all"):
+            r["traffic_source"] = ("profiles/ncu_traffic.json: DRAM read+write bytes per STEP summed over "
+                                   + w["kernel"].replace("+", ", ") + " (ncu)")
+            if w["bound"] == "hbm":
+                # executed view: the bytes the step really moved / its time, against the same peak
+                t_step = WORKLOADS[name]["N"] * w["steps_per_unit"] / units_per_s
+                r["executed_achieved"] = r["traffic"] / t_step / 1e9
+                r["executed_frac"] = r["executed_achieved"] / r["peak"]
+        else:
+            r["traffic_source"] = "profiles/ncu_traffic.json: DRAM read+write bytes per launch of the dominant kernel (ncu)"
     return r
 
 
@@ -380,8 +509,9 @@ def main():
     import parcompfin_b200 as pcf
     pcf.load_library()  # fails loudly when the CUDA extension is missing: there is no fallback
     job = dist.setup()
+    parity = None
     if job.world > 1:
-        dist.init_library(job)
+        parity = multi_gpu_parity(pcf, dist, job)   # outside the timed region; leaves the library up in its default mode
     else:
         pcf.init(args.gpus)  # single process: N GPUs driven in-process (N = 1 in the default run)
     n_gpus = pcf.world_size()
@@ -415,14 +545,27 @@ def main():
             if other == name:
                 continue
             try:
-                mo = measure(pcf, dist, job, other, 2, 3)
-                ups = mo["units"] * 2 / mo["device_s"]
+                wo = WORKLOADS[other]
+                k = 30 if wo.get("latency") else 2
+                mo = measure(pcf, dist, job, other, k, 3)
+                ups = mo["units"] * k / mo["device_s"]
                 others.append({"workload": WORKLOADS[other]["config"], "value": ups, "unit": WORKLOADS[other]["unit"],
-                               "e2e": mo["units"] * 2 / mo["wall_s"], "ms_per_step": 1e3 * mo["device_s"] / 2,
+                               "e2e": mo["units"] * k / mo["wall_s"], "ms_per_step": 1e3 * mo["device_s"] / k,
                                "price": mo["price"], "std_error": mo["se"], "gpu_launches": mo["launches"],
                                # a path that does not shard (the tree) runs as replicas: its rate is per GPU already
                                "roofline": roofline_for(other, ups if WORKLOADS[other].get("replicas") else ups / n_gpus,
                                                         fp64_peak, hbm, hbm_src)})
+                if wo.get("latency"):
+                    # launch-latency-bound sizes: microseconds per call, and the same for a ONE-unit call of the method
+                    # (the floor: launch, grid reduction, completion, result read-back and nothing else)
+                    fl = measure(pcf, dist, job, other, k, 3, N=2)
+                    others[-1]["latency_us"] = {
+                        "device": 1e6 * mo["device_s"] / k, "c_abi_call": 1e6 * mo["abi_s"] / k,
+                        "python_call": 1e6 * mo["wall_s"] / k,
+                        "floor_device": 1e6 * fl["device_s"] / k, "floor_c_abi_call": 1e6 * fl["abi_s"] / k,
+                        "note": "device = CUDA events around the kernel; c_abi_call = wall clock of the pcf_* call itself "
+                                "(parameter struct in, result out, one stream synchronise); python_call adds the ctypes "
+                                "binding; floor = the same call on 2 units"}
                 if "assets" in WORKLOADS[other]:  # the basket is also quoted in asset-steps
                     others[-1]["asset_steps_per_sec"] = ups * WORKLOADS[other]["assets"]
                 if job.rank == 0 and n_gpus == 1 and not args.no_cpu:
@@ -468,6 +611,8 @@ def main():
             "clocks": clocks,
             "others": others,
         }
+        if parity is not None:
+            line["parity"] = parity
         emit(line)
     dist.barrier(job)
     pcf.shutdown()

@@ -360,11 +360,16 @@ __device__ __forceinline__ DateRule make_rule(int mode, const double* s_coef, do
 // the terms of date m-1's moments (kMoments) or of the final sum (kFinal) added to run[] / cnt. Returns true when any of
 // the four dates changed. src = row m, sp = row m-1 (kMoments). colp + d*row_bytes is the address of paths[d][first path
 // of the quad]; s_disc[k] = exp(-r dt k), s_abs[k] = exp(-r k dt).
-template <typename WT, bool kMoments, bool kFinal>
+// `after_gathers()` runs once the gather loads have been issued and before their results are used: the persistent driver
+// releases its ring slot there, so that the TMA refill (17 KB per tile) queues BEHIND this warp's gathers instead of in
+// front of them -- the loop's time is the gathers' latency (ncu: the first FP64 instructions that consume them hold 40 %
+// of all stall samples), and that latency is mostly the refill traffic a gather has to wait behind.
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+template <typename WT, bool kMoments, bool kFinal, class Hook = NoHook>
 __device__ __forceinline__ bool sweep_quad(const double (&src)[4], const double (&sp)[4], int (&w)[4], bool live,
                                            const DateRule& R, int m, double sgn, double nE,
                                            const char* colp, size_t row_bytes, const double* s_disc,
-                                           const double* s_abs, double (&run)[8], int& cnt) {
+                                           const double* s_abs, double (&run)[8], int& cnt, Hook after_gathers = Hook()) {
   constexpr int kFlag = WhenBits<WT>::kFlag, kMask = WhenBits<WT>::kMask;
   const double* s_disc_m = s_disc - (m - 1);  // s_disc_m[d] = exp(-r dt (d - (m-1)))
   // cp*(S_m - E), cp*(S_{m-1} - E)
@@ -418,6 +423,7 @@ __device__ __forceinline__ bool sweep_quad(const double (&src)[4], const double 
     if (need[e] && d != m)
       gv[e] = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
   }
+  after_gathers();
   // (d) moments of date m-1 / final sum. Out-of-the-money (and dead) lanes add exact zeros.
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -649,8 +655,12 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persi
         // generic-proxy reads of the slot must be ordered before the TMA engine (async proxy) refills it: without
         // this fence a deep ring at 2 CTAs/SM produced stale reads (observed as run-to-run price noise)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
+        const bool late = (a.knobs & 16) != 0;
+        uint64_t* my_empty = &s_empty[s];
+        if (!late) {
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(my_empty);
+        }
         if (++s == kStages) { s = 0; ph ^= 1; }
         if (first) wv = WQ::splat(M);  // mc_amer.cpp:23-27 (the slot's date area was not filled)
         if (!live) wv = WQ::splat(m);  // dead quad (tail of the last tile): date m, no flag, never in the money
@@ -661,7 +671,13 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persi
         WQ::unpack(wv, w);
         WVec* wp = reinterpret_cast<WVec*>(when + c0t) + tid;
         const char* colp = colp0 + (size_t)c0t * 8;
-        const bool changed = sweep_quad<WT, !kFin, kFin>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes, s_disc, s_abs, run, cnt);
+        const bool changed = sweep_quad<WT, !kFin, kFin>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes, s_disc, s_abs,
+                                                         run, cnt, [&] {
+          if (late) {  // release the slot only now: the refill queues behind this warp's gathers
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(my_empty);
+          }
+        });
         if (first) {
           if (live) *wp = WQ::pack(w);                                          // initialise the state
         } else if (R.mode >= 2) {
@@ -941,6 +957,14 @@ static int launch_sweep_persistent(Ctx& c, const SweepPArgs& a, const PeerLink& 
   auto k = amer_sweep_persistent_kernel<WT, kStages>;
   const size_t dsm = (size_t)kStages * sweep_stage_bytes<WT>() + 2 * sizeof(double) * (a.M + 1);
   PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+  // pin the shared-memory carve-out to what kSweepCtasPerSM CTAs need (the rest stays L1 for the gathers) instead of
+  // leaving the split to the driver's per-launch heuristic
+  {
+    const size_t need = (size_t)kSweepCtasPerSM * (dsm + 3 * 1024);
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  }
   int per_sm = 0;
   PCF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kSweepBlock, dsm));
   if (per_sm < 1) {
