@@ -218,6 +218,11 @@ __device__ bool solve3_reference_order(const double* mom, double coef[3]) {
 // mom[0..7] = n_itm, Sx, Sx^2, Sx^3, Sx^4, Sy, Syx, Syx^2 with x = S - E, y = discounted cash flow; products are formed
 // exactly like the reference forms them (left to right, no FMA): only the summation order differs.
 constexpr int kMomFold = 16;  // tiles (64 paths per thread) between folds of the plain running sums
+#ifdef PCF_EXACT_MOMENT_PRODUCTS
+constexpr bool kContractMoments = false;  // every moment product rounded as the reference rounds it (mc_amer.cpp:51-57)
+#else
+constexpr bool kContractMoments = true;
+#endif
 constexpr int kTilePaths = 1024;
 constexpr int kSweepConsumers = 256;                    // 4 paths of every tile per consumer thread
 constexpr int kSweepBlock = kSweepConsumers + 32;       // + the producer warp
@@ -360,16 +365,11 @@ __device__ __forceinline__ DateRule make_rule(int mode, const double* s_coef, do
 // the terms of date m-1's moments (kMoments) or of the final sum (kFinal) added to run[] / cnt. Returns true when any of
 // the four dates changed. src = row m, sp = row m-1 (kMoments). colp + d*row_bytes is the address of paths[d][first path
 // of the quad]; s_disc[k] = exp(-r dt k), s_abs[k] = exp(-r k dt).
-// `after_gathers()` runs once the gather loads have been issued and before their results are used: the persistent driver
-// releases its ring slot there, so that the TMA refill (17 KB per tile) queues BEHIND this warp's gathers instead of in
-// front of them -- the loop's time is the gathers' latency (ncu: the first FP64 instructions that consume them hold 40 %
-// of all stall samples), and that latency is mostly the refill traffic a gather has to wait behind.
-struct NoHook { __device__ __forceinline__ void operator()() const {} };
-template <typename WT, bool kMoments, bool kFinal, class Hook = NoHook>
+template <typename WT, bool kMoments, bool kFinal>
 __device__ __forceinline__ bool sweep_quad(const double (&src)[4], const double (&sp)[4], int (&w)[4], bool live,
                                            const DateRule& R, int m, double sgn, double nE,
                                            const char* colp, size_t row_bytes, const double* s_disc,
-                                           const double* s_abs, double (&run)[8], int& cnt, Hook after_gathers = Hook()) {
+                                           const double* s_abs, double (&run)[8], int& cnt) {
   constexpr int kFlag = WhenBits<WT>::kFlag, kMask = WhenBits<WT>::kMask;
   const double* s_disc_m = s_disc - (m - 1);  // s_disc_m[d] = exp(-r dt (d - (m-1)))
   // cp*(S_m - E), cp*(S_{m-1} - E)
@@ -423,7 +423,6 @@ __device__ __forceinline__ bool sweep_quad(const double (&src)[4], const double 
     if (need[e] && d != m)
       gv[e] = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
   }
-  after_gathers();
   // (d) moments of date m-1 / final sum. Out-of-the-money (and dead) lanes add exact zeros.
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -433,16 +432,30 @@ __device__ __forceinline__ bool sweep_quad(const double (&src)[4], const double 
     if (kMoments) {
       const double x1 = ex[e];
       const double cont = __dmul_rn(s_disc_m[d], cs);  // d >= m: index in [1, M]
-      const double x2 = __dmul_rn(x1, x1), x3 = __dmul_rn(x2, x1), x4 = __dmul_rn(x3, x1);
-      const double yx = __dmul_rn(cont, x1), yx2 = __dmul_rn(yx, x1);
       cnt += need[e] ? 1 : 0;
-      run[1] += x1;
-      run[2] += x2;
-      run[3] += x3;
-      run[4] += x4;
-      run[5] += cont;
-      run[6] += yx;
-      run[7] += yx2;
+      if (kContractMoments) {
+        // 8 FP64 instructions instead of 13: x^3, x^4, y x, y x^2 enter their sums through one FMA each (x^4 as x^2 x^2,
+        // y x^2 as y (x^2)). Each product differs from the reference's left-to-right one by at most an ulp -- the same
+        // order as the reassociation of the sums themselves, far inside the 1e-12 replay tolerance.
+        const double x2 = __dmul_rn(x1, x1);
+        run[1] += x1;
+        run[2] += x2;
+        run[3] = fma(x2, x1, run[3]);
+        run[4] = fma(x2, x2, run[4]);
+        run[5] += cont;
+        run[6] = fma(cont, x1, run[6]);
+        run[7] = fma(cont, x2, run[7]);
+      } else {
+        const double x2 = __dmul_rn(x1, x1), x3 = __dmul_rn(x2, x1), x4 = __dmul_rn(x3, x1);
+        const double yx = __dmul_rn(cont, x1), yx2 = __dmul_rn(yx, x1);
+        run[1] += x1;
+        run[2] += x2;
+        run[3] += x3;
+        run[4] += x4;
+        run[5] += cont;
+        run[6] += yx;
+        run[7] += yx2;
+      }
     }
     if (kFinal) {
       // exercise_st (mc_amer.cpp:103): the regression branch booked payoff(x, E) = max(cp*(x - E), 0), x = S - E;
@@ -493,8 +506,8 @@ struct SweepPArgs {
   unsigned long long seq0;  // the iteration of date m publishes exchange seq0 + (M - m)
   unsigned long long* dbg;  // PCF_TUNING builds: cycle counters summed over CTAs (tools/tune_amer_persistent.py)
   int keep_last;            // row m-1 is loaded with L2 evict_last instead of evict_normal (see the producer)
-  int knobs;                // PCF_TUNING A/B bits: 1 producer waits with a suspend hint, 2 consumers too, 4 no reversal,
-                            // 8 back-off in the date-barrier poll
+  int knobs;                // A/B bits (PCF_TUNING builds; 1 otherwise): 1 producer waits with a suspend hint, 2 consumers
+                            // too, 4 no reversal of the tile walk, 8 back-off in the date-barrier poll
 };
 
 #ifdef PCF_TUNING
@@ -655,12 +668,8 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persi
         // generic-proxy reads of the slot must be ordered before the TMA engine (async proxy) refills it: without
         // this fence a deep ring at 2 CTAs/SM produced stale reads (observed as run-to-run price noise)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const bool late = (a.knobs & 16) != 0;
-        uint64_t* my_empty = &s_empty[s];
-        if (!late) {
-          __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(my_empty);
-        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
         if (++s == kStages) { s = 0; ph ^= 1; }
         if (first) wv = WQ::splat(M);  // mc_amer.cpp:23-27 (the slot's date area was not filled)
         if (!live) wv = WQ::splat(m);  // dead quad (tail of the last tile): date m, no flag, never in the money
@@ -672,12 +681,7 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persi
         WVec* wp = reinterpret_cast<WVec*>(when + c0t) + tid;
         const char* colp = colp0 + (size_t)c0t * 8;
         const bool changed = sweep_quad<WT, !kFin, kFin>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes, s_disc, s_abs,
-                                                         run, cnt, [&] {
-          if (late) {  // release the slot only now: the refill queues behind this warp's gathers
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(my_empty);
-          }
-        });
+                                                         run, cnt);
         if (first) {
           if (live) *wp = WQ::pack(w);                                          // initialise the state
         } else if (R.mode >= 2) {
@@ -955,7 +959,7 @@ static int launch_sweep(Ctx& c, bool final_date, int grid, int stages, const Swe
 template <typename WT, int kStages>
 static int launch_sweep_persistent(Ctx& c, const SweepPArgs& a, const PeerLink& link, long long ntiles) {
   auto k = amer_sweep_persistent_kernel<WT, kStages>;
-  const size_t dsm = (size_t)kStages * sweep_stage_bytes<WT>() + 2 * sizeof(double) * (a.M + 1);
+  const size_t dsm = (size_t)kStages * sweep_stage_bytes<WT>() + 2 * sizeof(double) * (a.M + 1);  // ring, tables
   PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
   // pin the shared-memory carve-out to what kSweepCtasPerSM CTAs need (the rest stays L1 for the gathers) instead of
   // leaving the split to the driver's per-launch heuristic

@@ -8,11 +8,8 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 pcf.init(1)
 for rep in range(3):
     for name, env in (("chain", {"PCF_AMER_CHAIN": "1"}),
-                      ("persistent 2st, early release", {"PCF_AMER_SWEEP": "2", "PCF_AMER_KNOBS": "1"}),
-                      ("persistent 2st, late release", {"PCF_AMER_SWEEP": "2", "PCF_AMER_KNOBS": "17"}),
-                      ("persistent 3st, early release", {"PCF_AMER_SWEEP": "3", "PCF_AMER_KNOBS": "1"}),
-                      ("persistent 3st, late release", {"PCF_AMER_SWEEP": "3", "PCF_AMER_KNOBS": "17"}),
-                      ("persistent 4st, late release", {"PCF_AMER_SWEEP": "4", "PCF_AMER_KNOBS": "17"})):
+                      ("persistent 2st", {"PCF_AMER_SWEEP": "2", "PCF_AMER_KNOBS": "1"}),
+                      ("persistent 3st", {"PCF_AMER_SWEEP": "3", "PCF_AMER_KNOBS": "1"})):
         for k in ("PCF_AMER_CHAIN", "PCF_AMER_SWEEP", "PCF_AMER_L2", "PCF_AMER_NOCOOP", "PCF_AMER_KNOBS"):
             os.environ.pop(k, None)
         os.environ.update(env)
