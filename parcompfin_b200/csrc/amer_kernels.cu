@@ -223,11 +223,16 @@ constexpr bool kContractMoments = false;  // every moment product rounded as the
 #else
 constexpr bool kContractMoments = true;
 #endif
-constexpr int kTilePaths = 1024;
-constexpr int kSweepConsumers = 256;                    // 4 paths of every tile per consumer thread
-constexpr int kSweepBlock = kSweepConsumers + 32;       // + the producer warp
+// Launch shape of the sweep: kWarps consumer warps (4 paths of every tile per consumer thread) + the producer warp,
+// kCtas CTAs per SM
+template <int kWarps_, int kCtas_>
+struct SweepShape {
+  static constexpr int kWarps = kWarps_, kCtas = kCtas_;
+  static constexpr int kConsumers = 32 * kWarps;
+  static constexpr int kBlock = kConsumers + 32;
+  static constexpr int kTile = 4 * kConsumers;  // paths per tile
+};
 constexpr int kMaxStages = 6;
-constexpr int kSweepCtasPerSM = 3;
 
 template <typename WT> struct WhenBits;
 template <> struct WhenBits<uint8_t> { static constexpr int kFlag = 0x80, kMask = 0x7f; };
@@ -284,7 +289,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kSweepConsumers) : "memory"); }
+template <int kConsumers>
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
 
 template <typename WT>
 __global__ void amer_fill_when_kernel(WT* __restrict__ when, long long Np, int M) {
@@ -361,6 +367,12 @@ __device__ __forceinline__ DateRule make_rule(int mode, const double* s_coef, do
   return R;
 }
 
+#ifdef PCF_TUNING
+// timing-only experiments (results are WRONG with any bit set): 1 no gathers, 2 no per-path work at all (the consumers
+// only pull the tile out of the ring), 4 no stores of exercise dates (tools/tune_amer_chain.py)
+__constant__ int c_sweep_knobs;
+#endif
+
 // One quad (4 consecutive paths, one 32-byte sector per row) at date m: the decision of date m on the dates w[], then
 // the terms of date m-1's moments (kMoments) or of the final sum (kFinal) added to run[] / cnt. Returns true when any of
 // the four dates changed. src = row m, sp = row m-1 (kMoments). colp + d*row_bytes is the address of paths[d][first path
@@ -420,6 +432,9 @@ __device__ __forceinline__ bool sweep_quad(const double (&src)[4], const double 
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int d = w[e] & kMask;
+#ifdef PCF_TUNING
+    if (c_sweep_knobs & 1) continue;
+#endif
     if (need[e] && d != m)
       gv[e] = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
   }
@@ -491,292 +506,9 @@ __device__ __forceinline__ void fold_runs(double (&run)[8], int& cnt, double2 (*
   }
 }
 
-// ----------------------------------------------------------------------------------------------------------------
-// Persistent driver: all dates in one cooperative launch.
-struct SweepPArgs {
-  const double* paths;  // row m-1 = date m, stride Np
-  void* when;
-  long long Np;         // multiple of 16
-  double E;
-  int cp, M, lsm;
-  double* partials;     // [grid][8][2]
-  unsigned int* ticket;
-  double* out;          // final (sum, sumsq), job-wide: host-mapped
-  int* err_flag;        // host-mapped status word
-  unsigned long long seq0;  // the iteration of date m publishes exchange seq0 + (M - m)
-  unsigned long long* dbg;  // PCF_TUNING builds: cycle counters summed over CTAs (tools/tune_amer_persistent.py)
-  int keep_last;            // row m-1 is loaded with L2 evict_last instead of evict_normal (see the producer)
-  int knobs;                // A/B bits (PCF_TUNING builds; 1 otherwise): 1 producer waits with a suspend hint, 2 consumers
-                            // too, 4 no reversal of the tile walk, 8 back-off in the date-barrier poll
-};
-
-#ifdef PCF_TUNING
-#define PCF_DBG_CLOCK(var) const long long var = clock64()
-#define PCF_DBG_ADD(acc, expr) acc += (expr)
-#else
-#define PCF_DBG_CLOCK(var)
-#define PCF_DBG_ADD(acc, expr)
-#endif
-
-template <typename WT>
-__host__ __device__ constexpr size_t sweep_stage_bytes() { return (size_t)kTilePaths * (8 + 8 + sizeof(WT)); }
-
-// The exercise dates of a tile reach the consumers through the ring like the rows do, which keeps the tile loop the one
-// of the per-date kernel (the first persistent build fetched them per thread -- a register prefetch that ptxas spilled
-// right after the load, then an asynchronous word copy -- and its tile loop swung between 22 and 30 ms from one build to
-// the next, profiles/r2_tune_amer_persistent.log). The dates of date m-1 are the consumers' own generic-proxy stores of
-// date m, read back by the TMA engine (async proxy): every consumer thread issues fence.proxy.async after its last store
-// of a date and its warp arrives on s_done; the producer issues the ROW copies of the first kStages tiles of the new date
-// as slots free up, waits for s_done, and only then issues their date copies (all later tiles of a date were written
-// before s_done completed, so they need no further care). Tiles are static per CTA (blockIdx.x + k * grid), so no other
-// CTA's stores are involved; the walk over them alternates direction from date to date, which makes the first tiles of
-// a date the ones whose rows were read last (L2) -- and exactly the ones the deferred copies cover.
-template <typename WT, int kStages>
-__global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_persistent_kernel(SweepPArgs a, PeerLink link) {
-  typedef WhenQuad<WT> WQ;
-  typedef typename WQ::Vec WVec;
-  constexpr size_t kStage = sweep_stage_bytes<WT>();
-  __shared__ double s_mom[kXchgVals];
-  __shared__ double s_coef[3];
-  __shared__ double s_pub[kXchgVals + 8];
-  __shared__ int s_mode, s_last;
-  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_done;
-  __shared__ double2 s_wacc[kSweepConsumers / 32][8];  // per-WARP compensated totals of the current date
-  extern __shared__ __align__(128) unsigned char dyn[];
-  unsigned char* ring = dyn;                                                   // kStages x kStage
-  double* s_disc = reinterpret_cast<double*>(dyn + (size_t)kStages * kStage);  // exp(-r dt k), k = 0..M
-  double* s_abs = s_disc + (a.M + 1);                                          // exp(-r k dt)
-  const int tid = threadIdx.x;
-  const int M = a.M;
-  for (int k = tid; k < 2 * (M + 1); k += blockDim.x) s_disc[k] = c_amer_tab[kDiscFwd + k];
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], kSweepConsumers / 32);
-    }
-    mbar_init(&s_done, kSweepConsumers / 32);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-
-  const long long Np = a.Np;
-  const long long ntiles = (Np + kTilePaths - 1) / kTilePaths;
-  const int nk = (blockIdx.x < ntiles) ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;  // this CTA's tiles
-  WT* when = reinterpret_cast<WT*>(a.when);
-
-  if (tid >= kSweepConsumers) {
-    // ---- producer warp: one elected lane keeps the ring full, across date boundaries
-    if (tid == kSweepConsumers) {
-      // row m is dead after this date (evict-first); row m-1 is read again at the next date, which starts where this
-      // one ends, so it keeps the default policy
-      uint64_t pol, pol_keep;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-      if (a.keep_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-      else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
-      uint32_t it = 0, done_parity = 0;
-      for (int m = M; m >= 1; --m) {
-        const bool first = (m == M);
-        const bool rev = ((M - m) & 1) != 0 && !(a.knobs & 4);
-        const double* row_m = a.paths + (size_t)(m - 1) * Np;
-        const double* row_p = a.paths + (size_t)(m > 1 ? m - 2 : 0) * Np;
-        const uint32_t per_path = (m > 1 ? 16u : 8u) + (first ? 0u : (uint32_t)sizeof(WT));
-        // tile kk of this date: waits for its slot, arms the barrier with the bytes of rows AND dates, copies the rows
-        // and -- unless deferred -- the dates
-        auto issue = [&](int kk, bool rows, bool dates) {
-          const long long c0 = (blockIdx.x + (long long)(rev ? nk - 1 - kk : kk) * gridDim.x) * kTilePaths;
-          const uint32_t n = (uint32_t)((Np - c0 < kTilePaths) ? (Np - c0) : kTilePaths);  // multiple of 16
-          const uint32_t slot = (it + (uint32_t)kk) % kStages, ph = ((it + (uint32_t)kk) / kStages) & 1u;
-          unsigned char* st = ring + (size_t)slot * kStage;
-          if (rows) {
-            mbar_wait(&s_empty[slot], ph ^ 1, (a.knobs & 1) ? 2000u : 0u);
-            mbar_arrive_expect_tx(&s_full[slot], n * per_path);
-            bulk_g2s(st, row_m + c0, n * 8u, &s_full[slot], pol);
-            if (m > 1) bulk_g2s(st + kTilePaths * 8, row_p + c0, n * 8u, &s_full[slot], pol_keep);
-          }
-          if (dates) bulk_g2s(st + kTilePaths * 16, when + c0, n * (uint32_t)sizeof(WT), &s_full[slot], pol_keep);
-        };
-        const int nd = first ? 0 : (nk < kStages ? nk : kStages);
-        for (int kk = 0; kk < nd; ++kk) issue(kk, true, false);   // rows early: they do not depend on date m+1
-        if (nd > 0) {
-          mbar_wait(&s_done, done_parity, (a.knobs & 1) ? 2000u : 0u);  // this CTA's stores of date m+1 are complete
-          done_parity ^= 1u;
-          asm volatile("fence.proxy.async;" ::: "memory");
-          for (int kk = 0; kk < nd; ++kk) issue(kk, false, true);
-        }
-        for (int kk = nd; kk < nk; ++kk) issue(kk, true, !first);
-        it += (uint32_t)nk;
-      }
-    }
-    return;
-  }
-
-  // ---- consumers: thread `tid` owns paths 4 tid .. 4 tid + 3 of every tile (one 32-byte sector per row)
-  const double sgn = (double)a.cp, nE = -sgn * a.E;
-  const size_t row_bytes = (size_t)Np * 8;
-  // address of paths[d][n] for this thread's first path of tile 0 is colp0 + d*row_bytes (row d-1 holds date d)
-  const char* colp0 = reinterpret_cast<const char*>(a.paths) + (size_t)tid * 32 - row_bytes;
-  int s = 0;
-  uint32_t ph = 0;
-#ifdef PCF_TUNING
-  long long dbg_wait = 0, dbg_tiles = 0, dbg_arrive = 0;
-  const long long dbg_t0 = clock64();
-#endif
-
-  for (int m = M; m >= 1; --m) {
-    const bool first = (m == M), final_date = (m == 1);
-    const bool rev = ((M - m) & 1) != 0 && !(a.knobs & 4);
-    if ((tid & 31) == 0) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s_wacc[tid >> 5][k] = make_double2(0.0, 0.0);
-    }
-    PCF_DBG_CLOCK(dbg_a);
-    if (!first) {
-      // moments of date m: every rank's publication (this GPU's own included) in this GPU's mailbox
-      if (tid < 32)
-        peer_gather_warp<kXchgVals>(link, a.seq0 + (unsigned long long)(M - m - 1), s_mom, (a.knobs & 8) ? 500u : 0u);
-      consumer_bar();
-      if (tid == 0) solve_date(s_mom, a.lsm, &s_mode, s_coef, a.err_flag);
-    } else if (tid == 0) {
-      s_mode = 0;
-    }
-    consumer_bar();
-    PCF_DBG_CLOCK(dbg_b);
-    const DateRule R = make_rule<WT>(s_mode, s_coef, sgn, nE, m);
-    // the tile loop, instantiated twice (dates M..2: moments of date m-1; date 1: the final sum) so that each loop is
-    // allocated for its own body
-    auto tiles = [&](auto final_tag) {
-      constexpr bool kFin = decltype(final_tag)::value;
-      double run[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) run[k] = 0.0;
-      int cnt = 0, fold = 0;
-      long long c0t = (blockIdx.x + (long long)(rev ? nk - 1 : 0) * gridDim.x) * kTilePaths;
-      const long long cstep = (rev ? -(long long)gridDim.x : (long long)gridDim.x) * kTilePaths;
-      for (int kk = 0; kk < nk; ++kk, c0t += cstep) {
-        const unsigned char* st = ring + (size_t)s * kStage;
-        const bool live = c0t + 4 * tid < Np;  // Np is a multiple of 16: a quad is live or dead as a whole
-        mbar_wait(&s_full[s], ph, (a.knobs & 2) ? 2000u : 0u);
-        const double2 sa = *reinterpret_cast<const double2*>(st + tid * 32);
-        const double2 sb = *reinterpret_cast<const double2*>(st + tid * 32 + 16);
-        double2 pa = make_double2(0.0, 0.0), pb = pa;
-        if (!kFin) {
-          pa = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32);
-          pb = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32 + 16);
-        }
-        WVec wv = *reinterpret_cast<const WVec*>(st + kTilePaths * 16 + tid * sizeof(WVec));
-        // generic-proxy reads of the slot must be ordered before the TMA engine (async proxy) refills it: without
-        // this fence a deep ring at 2 CTAs/SM produced stale reads (observed as run-to-run price noise)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
-        if (++s == kStages) { s = 0; ph ^= 1; }
-        if (first) wv = WQ::splat(M);  // mc_amer.cpp:23-27 (the slot's date area was not filled)
-        if (!live) wv = WQ::splat(m);  // dead quad (tail of the last tile): date m, no flag, never in the money
-
-        const double src[4] = {sa.x, sa.y, sb.x, sb.y};
-        const double sp[4] = {pa.x, pa.y, pb.x, pb.y};
-        int w[4];
-        WQ::unpack(wv, w);
-        WVec* wp = reinterpret_cast<WVec*>(when + c0t) + tid;
-        const char* colp = colp0 + (size_t)c0t * 8;
-        const bool changed = sweep_quad<WT, !kFin, kFin>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes, s_disc, s_abs,
-                                                         run, cnt);
-        if (first) {
-          if (live) *wp = WQ::pack(w);                                          // initialise the state
-        } else if (R.mode >= 2) {
-          if (__any_sync(0xffffffffu, changed) && live) *wp = WQ::pack(w);      // whole 128-byte lines back
-        } else if (changed) {
-          *wp = WQ::pack(w);
-        }
-        if (++fold == kMomFold) {
-          fold_runs<kFin ? 2 : 8, !kFin>(run, cnt, s_wacc, tid);
-          fold = 0;
-        }
-      }
-      fold_runs<kFin ? 2 : 8, !kFin>(run, cnt, s_wacc, tid);
-    };
-    if (final_date) tiles(std::true_type{});
-    else tiles(std::false_type{});
-    // this date's stores of exercise dates are complete: order them before the TMA engine's reads of the next date
-    asm volatile("fence.proxy.async;" ::: "memory");
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&s_done);
-    consumer_bar();
-    PCF_DBG_CLOCK(dbg_c);
-    PCF_DBG_ADD(dbg_wait, dbg_b - dbg_a);
-    PCF_DBG_ADD(dbg_tiles, dbg_c - dbg_b);
-
-    // ---- split grid barrier, arrival: CTA totals (one lane per moment, warps merged in order) -> global partials
-    if (tid < 32) {
-      if (tid < 8) {
-        Comp tot;
-#pragma unroll
-        for (int wq = 0; wq < kSweepConsumers / 32; ++wq) {
-          const double2 v = s_wacc[wq][tid];
-          tot.merge(Comp(v.x, v.y));
-        }
-        // back from cx-space to the reference's x = S - E: odd powers of x carry the sign of cp
-        const double f = (!final_date && (tid == 1 || tid == 3 || tid == 6)) ? sgn : 1.0;
-        a.partials[((size_t)blockIdx.x * 8 + tid) * 2 + 0] = tot.hi * f;
-        a.partials[((size_t)blockIdx.x * 8 + tid) * 2 + 1] = tot.lo * f;
-        __threadfence();
-      }
-      __syncwarp();
-      if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-    }
-    consumer_bar();
-    if (s_last) {
-      // ---- the last CTA to arrive folds all partials in block order and publishes (reduce.cuh grid_reduce, restated
-      // for the 8 consumer warps: the producer warp is busy refilling the ring and takes no part in barriers)
-      __threadfence();
-      {
-        // warp k folds moment k over all CTAs: lanes stride the blocks, then a fixed shuffle tree. The loads are issued
-        // as one batch (L2, independent) before the dependent chain of compensated adds
-        const int k = tid >> 5;
-        constexpr int kBatch = 8;
-        Comp acc;
-        for (unsigned int b0 = tid & 31; b0 < gridDim.x; b0 += 32 * kBatch) {
-          double2 v[kBatch];
-#pragma unroll
-          for (int j = 0; j < kBatch; ++j) {
-            const unsigned int b = b0 + 32 * j;
-            v[j] = (b < gridDim.x) ? __ldcg(reinterpret_cast<const double2*>(a.partials + ((size_t)b * 8 + k) * 2))
-                                   : make_double2(0.0, 0.0);
-          }
-#pragma unroll
-          for (int j = 0; j < kBatch; ++j) acc.merge(Comp(v[j].x, v[j].y));
-        }
-        acc = warp_reduce(acc);
-        if ((tid & 31) == 0) s_pub[k] = acc.value();
-      }
-      consumer_bar();
-      if (tid == 0) *a.ticket = 0u;
-      const unsigned long long seq_out = a.seq0 + (unsigned long long)(M - m);
-      peer_publish<kXchgVals>(link, seq_out, s_pub, consumer_bar);
-      if (final_date) {
-        consumer_bar();
-        if (tid < 32) peer_gather_warp<kXchgVals>(link, seq_out, s_pub + 8);
-        consumer_bar();
-        if (tid < 2) a.out[tid] = s_pub[8 + tid];
-      }
-    }
-    PCF_DBG_ADD(dbg_arrive, clock64() - dbg_c);
-  }
-#ifdef PCF_TUNING
-  if (tid == 0 && a.dbg) {  // sums and maxima over CTAs, in cycles: date-barrier wait, tile loops, arrival/fold, total
-    const long long tot = clock64() - dbg_t0;
-    atomicAdd(a.dbg + 0, (unsigned long long)dbg_wait);
-    atomicAdd(a.dbg + 1, (unsigned long long)dbg_tiles);
-    atomicAdd(a.dbg + 2, (unsigned long long)dbg_arrive);
-    atomicAdd(a.dbg + 3, (unsigned long long)tot);
-    atomicMax(a.dbg + 4, (unsigned long long)dbg_wait);
-    atomicMax(a.dbg + 5, (unsigned long long)dbg_tiles);
-    atomicMax(a.dbg + 6, (unsigned long long)tot);
-    atomicAdd(a.dbg + 7, 1ull);
-  }
-#endif
-}
+// one ring slot: a tile of row m, of row m-1 and of the exercise dates
+template <typename WT, int kTile>
+__host__ __device__ constexpr size_t sweep_stage_bytes() { return (size_t)kTile * (8 + 8 + sizeof(WT)); }
 
 // ----------------------------------------------------------------------------------------------------------------
 // Per-date driver (NCCL fallback path): one launch per exercise date; rows AND dates stream through the TMA ring.
@@ -796,25 +528,34 @@ struct SweepArgs {
   unsigned int* ticket;
   double* out;          // kMoments: the 8 moments of date m-1; kFinal: sum, sumsq
   int* err_flag;
+  unsigned int* tile_ctr;   // this date's tile counter (zero on entry): tiles beyond a CTA's first are handed out on
+                            // demand; null: tile k of CTA b is b + k * grid
+  unsigned long long* dbg;  // PCF_TUNING builds: per CTA (smid, consumer cycles in the tile loop, tiles), else null
 };
 
-template <typename WT, bool kMoments, bool kFinal>
-__global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_kernel(SweepArgs a, PeerLink link_out) {
+template <typename WT, bool kMoments, bool kFinal, class Shape>
+__global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel(SweepArgs a, PeerLink link) {
   typedef WhenQuad<WT> WQ;
   typedef typename WQ::Vec WVec;
-  constexpr size_t kStage = sweep_stage_bytes<WT>();
+  constexpr int kSweepConsumers = Shape::kConsumers, kTilePaths = Shape::kTile;
+  constexpr size_t kStage = sweep_stage_bytes<WT, kTilePaths>();
   constexpr int kSums = kFinal ? 2 : 8;
   __shared__ double smem[8 * 2 * 32];
   __shared__ double s_mom[kXchgVals];
   __shared__ double s_coef[3];
   __shared__ int s_mode;
   __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages];
+  __shared__ long long s_tile[kMaxStages];  // tile held by each ring slot, -1: no more tiles
   __shared__ double2 s_wacc[kSweepConsumers / 32][8];
   extern __shared__ __align__(128) unsigned char dyn[];
   unsigned char* ring = dyn;                                                     // stages x kStage
   double* s_disc = reinterpret_cast<double*>(dyn + (size_t)a.stages * kStage);   // exp(-r dt k), k = 0..M
   double* s_abs = s_disc + (a.M + 1);                                            // exp(-r k dt) (kFinal)
   const int tid = threadIdx.x;
+  // Programmatic dependent launch: the kernel of date m-1 may be scheduled as soon as every CTA of this one has started
+  // (its CTAs become resident as ours exit, stage their tables, pull the rows of their first tiles and park in
+  // griddepcontrol.wait until this grid has completed and its stores -- dates, moments -- are visible)
+  asm volatile("griddepcontrol.launch_dependents;");
   if (tid < (kSweepConsumers / 32) * 8) s_wacc[tid / 8][tid % 8] = make_double2(0.0, 0.0);
   for (int k = tid; k <= a.M; k += blockDim.x) {
     s_disc[k] = c_amer_tab[kDiscFwd + k];
@@ -840,36 +581,75 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_kerne
   WT* when = reinterpret_cast<WT*>(a.when);
 
   if (tid >= kSweepConsumers) {
-    // ---- producer warp: one elected lane keeps the ring full; it starts before the moments of date m are read
+    // ---- producer warp: one elected lane keeps the ring full
     if (tid == kSweepConsumers) {
       uint64_t pol, pol_keep;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
       asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
-      int s = 0;
-      uint32_t ph = 0;
-      for (long long tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
-        const long long t = a.rev ? ntiles - 1 - tt : tt;
-        mbar_wait(&s_empty[s], ph ^ 1);
-        const long long c0 = t * kTilePaths;
+      constexpr uint32_t kPerPath = 8 + (kMoments ? 8 : 0) + sizeof(WT);
+      // The first tile of a CTA is its block index; the others come off the date's counter as ring slots free up, so a
+      // CTA on a slow SM simply takes fewer of them (with a fixed b + k*grid assignment every date waits for the slowest
+      // SM: the per-CTA tile-loop times of one date spread by ~15 %, profiles/r2_tune_amer_chain.log). The next index
+      // is requested one tile ahead, so the atomic's round trip hides behind the wait for the slot.
+      long long cur = blockIdx.x;
+      auto next_tile = [&](long long prev) -> long long {
+        return a.tile_ctr ? (long long)gridDim.x + (long long)atomicAdd(a.tile_ctr, 1u) : prev + (long long)gridDim.x;
+      };
+      auto rows = [&](int slot, long long tt) {
+        const long long c0 = (a.rev ? ntiles - 1 - tt : tt) * kTilePaths;
         const uint32_t n = (uint32_t)((Np - c0 < kTilePaths) ? (Np - c0) : kTilePaths);  // multiple of 16
-        unsigned char* st = ring + (size_t)s * kStage;
-        mbar_arrive_expect_tx(&s_full[s], n * (uint32_t)(8 + (kMoments ? 8 : 0) + sizeof(WT)));
-        bulk_g2s(st, row_m + c0, n * 8u, &s_full[s], pol);
-        if (kMoments) bulk_g2s(st + kTilePaths * 8, row_p + c0, n * 8u, &s_full[s], pol_keep);
-        bulk_g2s(st + kTilePaths * 16, when + c0, n * (uint32_t)sizeof(WT), &s_full[s], pol_keep);
+        unsigned char* st = ring + (size_t)slot * kStage;
+        s_tile[slot] = c0;
+        mbar_arrive_expect_tx(&s_full[slot], n * kPerPath);
+        bulk_g2s(st, row_m + c0, n * 8u, &s_full[slot], pol);
+        if (kMoments) bulk_g2s(st + kTilePaths * 8, row_p + c0, n * 8u, &s_full[slot], pol_keep);
+      };
+      auto dates = [&](int slot) {
+        const long long c0 = s_tile[slot];
+        const uint32_t n = (uint32_t)((Np - c0 < kTilePaths) ? (Np - c0) : kTilePaths);
+        bulk_g2s(ring + (size_t)slot * kStage + kTilePaths * 16, when + c0, n * (uint32_t)sizeof(WT), &s_full[slot], pol_keep);
+      };
+      // rows do not depend on the previous date's kernel: the first tiles' rows are in flight before the wait; their
+      // exercise dates -- that kernel's stores -- follow it
+      int npre = 0;
+      while (npre < a.stages && cur < ntiles) {
+        rows(npre, cur);
+        cur = next_tile(cur);
+        ++npre;
+      }
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      for (int i = 0; i < npre; ++i) dates(i);
+      int s = (npre == a.stages) ? 0 : npre;
+      uint32_t ph = (npre == a.stages) ? 1u : 0u;
+      for (;;) {
+        mbar_wait(&s_empty[s], ph ^ 1);
+        if (cur >= ntiles) {
+          s_tile[s] = -1;
+          mbar_arrive(&s_full[s]);
+          break;
+        }
+        const long long nxt = next_tile(cur);
+        rows(s, cur);
+        dates(s);
+        cur = nxt;
         if (++s == a.stages) { s = 0; ph ^= 1; }
       }
     }
   } else {
     // ---- consumers
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (!a.first) {
-      if (tid < kXchgVals) s_mom[tid] = a.mom_in[tid];  // all-reduced by NCCL between the two launches
-      consumer_bar();
+      if (link.world > 1) {
+        if (tid < 32) peer_gather_warp<kXchgVals>(link, link.seq - 1ull, s_mom);  // every rank's moments of date m
+      } else if (tid < kXchgVals) {
+        s_mom[tid] = a.mom_in[tid];  // the previous launch's sums (all-reduced by NCCL in between when world > 1)
+      }
+      consumer_bar<kSweepConsumers>();
       if (tid == 0) solve_date(s_mom, a.lsm, &s_mode, s_coef, a.err_flag);
     } else if (tid == 0) {
       s_mode = 0;
     }
-    consumer_bar();
+    consumer_bar<kSweepConsumers>();
     const double sgn = (double)cp, nE = -sgn * E;
     const DateRule R = make_rule<WT>(s_mode, s_coef, sgn, nE, m);
     double run[8];
@@ -880,12 +660,16 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_kerne
     const char* colp0 = reinterpret_cast<const char*>(paths) + (size_t)tid * 32 - row_bytes;
     int s = 0;
     uint32_t ph = 0;
-    for (long long tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
-      const long long t = a.rev ? ntiles - 1 - tt : tt;
+#ifdef PCF_TUNING
+    const long long dbg_t0 = clock64();
+    int dbg_tiles = 0;
+#endif
+    for (;;) {
       const unsigned char* st = ring + (size_t)s * kStage;
-      const long long c0t = t * kTilePaths;
-      const bool live = c0t + 4 * tid < Np;
       mbar_wait(&s_full[s], ph);
+      const long long c0t = s_tile[s];
+      if (c0t < 0) break;
+      const bool live = c0t + 4 * tid < Np;
       const double2 sa = *reinterpret_cast<const double2*>(st + tid * 32);
       const double2 sb = *reinterpret_cast<const double2*>(st + tid * 32 + 16);
       double2 pa = make_double2(0.0, 0.0), pb = pa;
@@ -901,6 +685,9 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_kerne
       if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
       if (++s == a.stages) { s = 0; ph ^= 1; }
       if (!live) wv = WQ::splat(m);
+#ifdef PCF_TUNING
+      ++dbg_tiles;
+#endif
 
       const double src[4] = {sa.x, sa.y, sb.x, sb.y};
       const double sp[4] = {pa.x, pa.y, pb.x, pb.y};
@@ -908,8 +695,17 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_kerne
       WQ::unpack(wv, w);
       WVec* wp = reinterpret_cast<WVec*>(when + c0t) + tid;
       const char* colp = colp0 + (size_t)c0t * 8;
-      const bool changed = sweep_quad<WT, kMoments, kFinal>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes,
-                                                            s_disc, s_abs, run, cnt);
+#ifdef PCF_TUNING
+      if (c_sweep_knobs & 2) {
+        run[1] += src[0] + src[1] + src[2] + src[3] + sp[0] + sp[1] + sp[2] + sp[3] + (double)w[0];
+        continue;
+      }
+#endif
+      bool changed = sweep_quad<WT, kMoments, kFinal>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes,
+                                                      s_disc, s_abs, run, cnt);
+#ifdef PCF_TUNING
+      if (c_sweep_knobs & 4) changed = false;
+#endif
       if (R.mode >= 2) {
         if (__any_sync(0xffffffffu, changed) && live) *wp = WQ::pack(w);
       } else if (changed) {
@@ -921,6 +717,15 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_kerne
       }
     }
     fold_runs<kSums, kMoments>(run, cnt, s_wacc, tid);
+#ifdef PCF_TUNING
+    if (tid == 0 && a.dbg) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      a.dbg[blockIdx.x * 3 + 0] = smid;
+      a.dbg[blockIdx.x * 3 + 1] = (unsigned long long)(clock64() - dbg_t0);
+      a.dbg[blockIdx.x * 3 + 2] = (unsigned long long)dbg_tiles;
+    }
+#endif
   }
   // warp totals -> block -> grid (block_reduce's own first stage sees one meaningful lane per warp)
   Comp acc[kSums];
@@ -938,58 +743,108 @@ __global__ void __launch_bounds__(kSweepBlock, kSweepCtasPerSM) amer_sweep_kerne
     acc[6].hi *= sgn; acc[6].lo *= sgn;
   }
   __syncthreads();
-  grid_reduce<kSums>(acc, smem, a.partials, a.ticket, a.out, &link_out);
+  grid_reduce<kSums>(acc, smem, a.partials, a.ticket, a.out, &link);
 }
 
-template <typename WT>
-static int launch_sweep(Ctx& c, bool final_date, int grid, int stages, const SweepArgs& a, const PeerLink& lo) {
-  const size_t dsm = (size_t)stages * sweep_stage_bytes<WT>() + 2 * sizeof(double) * (a.M + 1);
+#ifdef PCF_TUNING
+static unsigned long long* g_sweep_dbg = nullptr;
+#endif
+
+template <typename WT, class Shape>
+static int launch_sweep(Ctx& c, bool final_date, bool dependent, int grid, int stages, const SweepArgs& a,
+                        const PeerLink& link) {
+  const size_t dsm = (size_t)stages * sweep_stage_bytes<WT, Shape::kTile>() + 2 * sizeof(double) * (a.M + 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(Shape::kBlock);
+  cfg.dynamicSmemBytes = dsm;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = dependent ? 1 : 0;
   if (final_date) {
-    auto k = amer_sweep_kernel<WT, false, true>;
+    auto k = amer_sweep_kernel<WT, false, true, Shape>;
     PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-    k<<<grid, kSweepBlock, dsm, c.stream>>>(a, lo);
+    PCF_CUDA(cudaLaunchKernelEx(&cfg, k, a, link));
   } else {
-    auto k = amer_sweep_kernel<WT, true, false>;
+    auto k = amer_sweep_kernel<WT, true, false, Shape>;
     PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-    k<<<grid, kSweepBlock, dsm, c.stream>>>(a, lo);
+    PCF_CUDA(cudaLaunchKernelEx(&cfg, k, a, link));
   }
-  return PCF_OK;
-}
-
-template <typename WT, int kStages>
-static int launch_sweep_persistent(Ctx& c, const SweepPArgs& a, const PeerLink& link, long long ntiles) {
-  auto k = amer_sweep_persistent_kernel<WT, kStages>;
-  const size_t dsm = (size_t)kStages * sweep_stage_bytes<WT>() + 2 * sizeof(double) * (a.M + 1);  // ring, tables
-  PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-  // pin the shared-memory carve-out to what kSweepCtasPerSM CTAs need (the rest stays L1 for the gathers) instead of
-  // leaving the split to the driver's per-launch heuristic
-  {
-    const size_t need = (size_t)kSweepCtasPerSM * (dsm + 3 * 1024);
-    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
-    if (pct > 100) pct = 100;
-    PCF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-  }
-  int per_sm = 0;
-  PCF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kSweepBlock, dsm));
-  if (per_sm < 1) {
-    set_last_error("mc_amer: the sweep kernel does not fit on this device");
-    return PCF_ECUDA;
-  }
-  // every CTA must be resident for the in-kernel date barrier: cooperative launch, grid <= what the device holds
-  long long grid = std::min<long long>(ntiles, (long long)c.sm_count * std::min(per_sm, kSweepCtasPerSM));
-  if (grid < 1) grid = 1;  // an empty shard still takes part in every exchange
-  SweepPArgs args = a;
-  PeerLink l = link;
-  void* params[] = {(void*)&args, (void*)&l};
-  if (tuning_env("PCF_AMER_NOCOOP")) {  // A/B: plain launch (the grid fits the device, so every CTA is resident anyway)
-    k<<<dim3((unsigned)grid), dim3(kSweepBlock), dsm, c.stream>>>(args, l);
-    return PCF_OK;
-  }
-  PCF_CUDA(cudaLaunchCooperativeKernel((const void*)k, dim3((unsigned)grid), dim3(kSweepBlock), params, dsm, c.stream));
   return PCF_OK;
 }
 
 static inline size_t amer_when_bytes(int M) { return M <= WhenBits<uint8_t>::kMask ? 1 : 2; }
+static inline size_t amer_when_area(long long Np, int M) { return ((size_t)Np * amer_when_bytes(M) + 255) & ~(size_t)255; }
+
+constexpr int kDefaultSweepShape = 231, kDefaultSweepStages = 2;
+
+// Per-date chain: one launch per exercise date, each a programmatic dependent of the one before. The moments travel
+// through the NVLink mailboxes (published by the last block of date m+1's kernel, gathered by every CTA of date m's),
+// through `mom` on one GPU, or through an ncclAllReduce between two launches on the fallback path.
+template <class Shape>
+static int run_sweep_chain(Ctx& c, const pcf_params& p, const double* paths, void* when, long long Np, int stages) {
+  const int M = p.M;
+  const long long ntiles = (Np + Shape::kTile - 1) / Shape::kTile;
+  const bool w8 = amer_when_bytes(M) == 1;
+  const bool nccl_path = c.world > 1 && !use_peer(c);
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)c.sm_count * Shape::kCtas));
+  unsigned int* tile_ctr = reinterpret_cast<unsigned int*>((char*)when + amer_when_area(Np, M));
+  PCF_CUDA(cudaMemsetAsync(tile_ctr, 0, sizeof(unsigned int) * (size_t)(M + 1), c.stream));
+  {
+    const int fg = grid_for(c, Np, 256, 8);
+    if (w8) amer_fill_when_kernel<uint8_t><<<fg, 256, 0, c.stream>>>((uint8_t*)when, Np, M);
+    else amer_fill_when_kernel<uint16_t><<<fg, 256, 0, c.stream>>>((uint16_t*)when, Np, M);
+    c.launches++;
+  }
+  SweepArgs sa;
+  sa.paths = paths; sa.when = when; sa.Np = Np; sa.E = p.E; sa.cp = p.cp; sa.M = M;
+  sa.lsm = (p.flags & PCF_FLAG_AMER_LSM) ? 1 : 0;
+  sa.stages = stages;
+  sa.partials = c.d_partials; sa.ticket = c.d_ticket; sa.err_flag = c.flag_dev;
+  sa.dbg = nullptr;
+  const bool dynamic_tiles = tuning_env("PCF_AMER_ONDEMAND") != nullptr;
+  const bool pdl = !nccl_path && tuning_env("PCF_AMER_NOPDL") == nullptr;
+#ifdef PCF_TUNING
+  {
+    const int knobs = tuning_env("PCF_AMER_ENVELOPE") ? atoi(tuning_env("PCF_AMER_ENVELOPE")) : 0;
+    PCF_CUDA(cudaMemcpyToSymbolAsync(c_sweep_knobs, &knobs, sizeof(int), 0, cudaMemcpyHostToDevice, c.stream));
+  }
+  if (!g_sweep_dbg) PCF_CUDA(cudaMalloc(&g_sweep_dbg, sizeof(unsigned long long) * 3 * 1024));
+  const int dbg_date = tuning_env("PCF_AMER_DBG_DATE") ? atoi(tuning_env("PCF_AMER_DBG_DATE")) : M / 2;
+#endif
+  double* mom[2] = {c.d_out + 8, c.d_out + 16};
+  for (int m = M; m >= 1; --m) {
+    sa.m = m;
+    sa.first = (m == M);
+    sa.rev = (M - m) & 1;
+    sa.mom_in = mom[m & 1];
+    sa.tile_ctr = dynamic_tiles ? tile_ctr + m : nullptr;
+#ifdef PCF_TUNING
+    sa.dbg = (m == dbg_date && grid <= 1024) ? g_sweep_dbg : nullptr;
+#endif
+    if (m < M) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));  // no-op unless this is the NCCL path
+    sa.out = (m > 1) ? mom[(m - 1) & 1] : final_out(c);
+    PeerLink l = c.link;
+    l.host_err = c.perr_dev;
+    l.call_first = c.call_first;
+    l.call_last = c.call_last;
+    l.gather = (m == 1) ? 1 : 0;  // the final sums: the publishing block also collects them (reduce.cuh)
+    if (use_peer(c)) {
+      l.seq = c.call_first + (unsigned long long)(M - m);  // published by this launch; it consumes seq - 1
+    } else {
+      l.world = 1;
+      l.seq = 0;
+    }
+    if (w8) PCF_TRY((launch_sweep<uint8_t, Shape>(c, m == 1, pdl && m < M, grid, stages, sa, l)));
+    else PCF_TRY((launch_sweep<uint16_t, Shape>(c, m == 1, pdl && m < M, grid, stages, sa, l)));
+    c.launches++;
+  }
+  PCF_CUDA(cudaGetLastError());
+  return PCF_OK;
+}
 
 // Host driver for one GPU. Enqueues everything on c.stream; the job-wide (sum, sumsq) of the discounted cash flows lands
 // in final_out(c)[0..1] (NCCL path: this GPU's partial sums in c.d_out[0..1]); c.d_out[8..23] holds the per-date moment
@@ -1067,87 +922,41 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
 
   // Backward sweep m = M .. 1 (mc_amer.cpp:23-27, 31, 109-111). The iteration of date m consumes the moments of date m
   // and produces those of date m-1 (date 1: the final sums).
-  const long long ntiles = (Np + kTilePaths - 1) / kTilePaths;
-  const bool w8 = amer_when_bytes(M) == 1;
-  const bool nccl_path = c.world > 1 && !use_peer(c);
-  const bool chain = nccl_path || tuning_env("PCF_AMER_CHAIN") != nullptr;
-  // ring depth 2 for both drivers: a third stage measured slower in the per-date chain
-  // (profiles/r1l_tune_amer_sweep_variants.log) and the same in the persistent kernel (profiles/r2_tune_amer_persistent.log)
-  int stages = 0;
+  int shape = kDefaultSweepShape, stages = kDefaultSweepStages;
+  if (const char* v = tuning_env("PCF_AMER_SHAPE")) shape = atoi(v);   // <consumer warps><CTAs per SM>
   if (const char* v = tuning_env("PCF_AMER_SWEEP")) stages = std::max(2, std::min(kMaxStages, atoi(v)));
-  if (!chain) {
-    // ONE cooperative launch; moments travel through the mailboxes (this GPU's own when it is alone)
-    SweepPArgs sp;
-    sp.paths = paths; sp.when = when; sp.Np = Np; sp.E = p.E; sp.cp = p.cp; sp.M = M;
-    sp.lsm = (p.flags & PCF_FLAG_AMER_LSM) ? 1 : 0;
-    sp.partials = c.d_partials; sp.ticket = c.d_ticket; sp.out = c.res_dev; sp.err_flag = c.flag_dev;
-    sp.dbg = nullptr;
-    sp.keep_last = tuning_env("PCF_AMER_L2") ? atoi(tuning_env("PCF_AMER_L2")) : 0;
-    sp.knobs = tuning_env("PCF_AMER_KNOBS") ? atoi(tuning_env("PCF_AMER_KNOBS")) : 1;
+  switch (shape) {
 #ifdef PCF_TUNING
-    sp.dbg = reinterpret_cast<unsigned long long*>(c.d_out + 24);  // read back with pcf_debug_counters()
-    PCF_CUDA(cudaMemsetAsync(sp.dbg, 0, 8 * sizeof(unsigned long long), c.stream));
+    case 83: return run_sweep_chain<SweepShape<8, 3>>(c, p, paths, when, Np, stages);
+    case 122: return run_sweep_chain<SweepShape<12, 2>>(c, p, paths, when, Np, stages);
+    case 161: return run_sweep_chain<SweepShape<16, 1>>(c, p, paths, when, Np, stages);
+    case 201: return run_sweep_chain<SweepShape<20, 1>>(c, p, paths, when, Np, stages);
+    case 281: return run_sweep_chain<SweepShape<28, 1>>(c, p, paths, when, Np, stages);
+    case 112: return run_sweep_chain<SweepShape<11, 2>>(c, p, paths, when, Np, stages);
+    case 73: return run_sweep_chain<SweepShape<7, 3>>(c, p, paths, when, Np, stages);
+    case 241: return run_sweep_chain<SweepShape<24, 1>>(c, p, paths, when, Np, stages);
 #endif
-    sp.seq0 = c.xchg_seq + 1;
-    c.xchg_seq += (unsigned long long)M;  // M exchanges, whether or not other ranks exist
-    PeerLink l = c.link;
-    l.host_err = c.perr_dev;
-    l.gather = 0;
-    l.seq = 0;
-    l.call_first = c.call_first;
-    l.call_last = c.call_last;
-    if (c.world <= 1) { l.world = 1; l.rank = 0; l.peer[0] = c.mailbox; }
-#ifdef PCF_TUNING
-    if (stages == 3) {
-      if (w8) PCF_TRY((launch_sweep_persistent<uint8_t, 3>(c, sp, l, ntiles)));
-      else PCF_TRY((launch_sweep_persistent<uint16_t, 3>(c, sp, l, ntiles)));
-    } else if (stages == 4) {
-      if (w8) PCF_TRY((launch_sweep_persistent<uint8_t, 4>(c, sp, l, ntiles)));
-      else PCF_TRY((launch_sweep_persistent<uint16_t, 4>(c, sp, l, ntiles)));
-    } else
-#endif
-    if (w8) PCF_TRY((launch_sweep_persistent<uint8_t, 2>(c, sp, l, ntiles)));
-    else PCF_TRY((launch_sweep_persistent<uint16_t, 2>(c, sp, l, ntiles)));
-    c.launches++;
-    PCF_CUDA(cudaGetLastError());
-    return PCF_OK;
+    case 231: return run_sweep_chain<SweepShape<23, 1>>(c, p, paths, when, Np, stages);
   }
-  // Per-date chain: an all-reduce of the 8 doubles between two launches (NCCL), or -- PCF_AMER_CHAIN in a tuning build,
-  // one GPU -- the round-1 baseline of the persistent kernel.
-  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)c.sm_count * kSweepCtasPerSM));
-  {
-    const int fg = grid_for(c, Np, 256, 8);
-    if (w8) amer_fill_when_kernel<uint8_t><<<fg, 256, 0, c.stream>>>((uint8_t*)when, Np, M);
-    else amer_fill_when_kernel<uint16_t><<<fg, 256, 0, c.stream>>>((uint16_t*)when, Np, M);
-    c.launches++;
-  }
-  SweepArgs sa;
-  sa.paths = paths; sa.when = when; sa.Np = Np; sa.E = p.E; sa.cp = p.cp; sa.M = M;
-  sa.lsm = (p.flags & PCF_FLAG_AMER_LSM) ? 1 : 0;
-  sa.stages = stages ? stages : 2;
-  sa.partials = c.d_partials; sa.ticket = c.d_ticket; sa.err_flag = c.flag_dev;
-  double* mom[2] = {c.d_out + 8, c.d_out + 16};
-  PeerLink none = c.link;
-  none.world = 1;
-  none.gather = 0;
-  for (int m = M; m >= 1; --m) {
-    sa.m = m;
-    sa.first = (m == M);
-    sa.rev = (M - m) & 1;
-    sa.mom_in = mom[m & 1];
-    if (m < M) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));
-    sa.out = (m > 1) ? mom[(m - 1) & 1] : final_out(c);
-    if (w8) PCF_TRY(launch_sweep<uint8_t>(c, m == 1, grid, sa.stages, sa, none));
-    else PCF_TRY(launch_sweep<uint16_t>(c, m == 1, grid, sa.stages, sa, none));
-    c.launches++;
-  }
-  PCF_CUDA(cudaGetLastError());
-  return PCF_OK;
+  set_last_error("unknown PCF_AMER_SHAPE");
+  return PCF_EINVAL;
 }
+
+#ifdef PCF_TUNING
+// Tuning builds only: (smid, consumer cycles in the tile loop, tiles) of every CTA of one date's sweep kernel
+extern "C" __attribute__((visibility("default"))) int pcf_debug_sweep(unsigned long long* out, int n) {
+  if (!g_sweep_dbg) return PCF_ENOINIT;
+  return cudaMemcpy(out, g_sweep_dbg, sizeof(unsigned long long) * (size_t)std::min(n, 3 * 1024), cudaMemcpyDeviceToHost) ==
+                 cudaSuccess
+             ? PCF_OK
+             : PCF_ECUDA;
+}
+#endif
 
 size_t amer_workspace_bytes(long long local_pairs, int M) {
   size_t Np = (2 * (size_t)local_pairs + 15) & ~(size_t)15;
-  return (size_t)M * Np * 8 + Np * amer_when_bytes(M) + 256;
+  // paths, exercise dates, one tile counter per date
+  return (size_t)M * Np * 8 + amer_when_area((long long)Np, M) + sizeof(unsigned int) * (size_t)(M + 1) + 256;
 }
 
 }  // namespace pcf

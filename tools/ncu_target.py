@@ -19,5 +19,8 @@ for i in range(reps):
                           weights=rng.dirichlet(np.ones(16)), cov=B @ B.T / 16 + .2 * np.eye(16), seed=i)
     elif name == "mc_amer": r = pcf.mc_amer(*a, N, 50, "put", seed=i)
     elif name == "binom_embar": r = pcf.binom(*a, N, "call")
+    elif name == "binom_embar_noscreen": r = pcf.binom(*a, N, "call", screen=False)
+    elif name == "tree_eur": r = pcf.binom_vanilla_eur(*a, N, "put")
+    elif name == "tree_amer": r = pcf.binom_vanilla_amer(*a, N, "put")
     print(name, N, r.price, r.seconds_kernel, r.units / r.seconds_kernel)
 pcf.shutdown()
