@@ -17,15 +17,16 @@
 // (one 32-byte sector, shared by neighbours with the same date). Round-1 builds carried the gathered value in a
 // `cash[n]` array instead: 16 B/path-date of extra read+write traffic, 38.8 B/path-date in total against ~18 B now.
 //
-// Rows and `when` are padded to a multiple of 16 paths (Np) with never-in-the-money dummies so that every TMA
-// bulk copy (rows and dates) is a whole number of 16-byte granules.
+// Rows and `when` are padded to a whole number of sweep tiles (Np, a multiple of 2944 paths in the shipped shape) with
+// never-in-the-money dummies, so that every TMA bulk copy is a complete tile and no quad needs a bounds test.
 //
-// Backward sweep: ONE persistent kernel walks the exercise dates m = M .. 1. At date m every CTA (a) waits for the
-// moments of date m (every rank's, its own included, arriving in this GPU's mailbox), solves the 3x3 normal equations
-// in the reference's operation order without FMA contraction, (b) applies the exercise decision of date m to the dates
-// held in registers, (c) accumulates the regression moments of date m-1 from that updated state and row m-1, and
-// (d) the last CTA to finish publishes them. Date 1 accumulates the final discounted sum (mc_amer.cpp:109-111) instead
-// of (c); date M initialises the state (mc_amer.cpp:23-27) instead of (a)-(b). See the sweep section below.
+// Backward sweep: one kernel per exercise date m = M .. 1, each launched as a programmatic dependent of the one before.
+// The kernel of date m (a) takes the moments of date m (the previous launch's sums on one GPU, every rank's
+// publication in this GPU's NVLink mailbox on several, the all-reduced buffer on the NCCL fallback path) and solves the
+// 3x3 normal equations in the reference's operation order without FMA contraction, (b) applies the exercise decision of
+// date m to the dates of each tile, (c) accumulates the regression moments of date m-1 from that updated state and row
+// m-1, and (d) its last CTA folds the per-CTA sums in block order and publishes them. Date 1 accumulates the final
+// discounted sum (mc_amer.cpp:109-111) instead of (c); date M decides nothing (mc_amer.cpp:23-27).
 #include "common.cuh"
 #include "reduce.cuh"
 #include "rng.cuh"
@@ -205,18 +206,17 @@ __device__ bool solve3_reference_order(const double* mom, double coef[3]) {
 }
 
 // ---- a7 (mc_amer.cpp:41-106): the backward sweep --------------------------------------------------------------
-// Two drivers share one per-quad body (sweep_quad):
-//   * amer_sweep_persistent_kernel: ONE cooperative launch walks all M dates (default: one GPU, and several GPUs with
-//     the NVLink mailboxes). Between two dates the grid meets at a split barrier: every CTA leaves its 8 compensated
-//     partial sums in global memory and takes a ticket; the CTA that takes the last one folds them in block order and
-//     publishes the moments of date m-1 to every rank's mailbox (its own included); every CTA then waits for all ranks'
-//     flags, adds the world x 8 values in rank order and solves the 3x3 system. While it waits, its producer warp has
-//     already refilled the TMA ring with the first tiles of rows m-1 / m-2 -- the bulk copies do not depend on the
-//     moments -- so a date boundary costs the barrier's latency, not a pipeline drain plus a kernel launch.
-//   * amer_sweep_kernel: one launch per date, used when the moments travel by ncclAllReduce between two kernels
-//     (PCF_NO_PEER / no peer mapping), and the round-1 baseline of the A/B measurement.
+// amer_sweep_kernel, one launch per date. A CTA is 23 consumer warps + 1 producer warp, ONE CTA per SM (24 warps let
+// ptxas have 80 registers, which the per-quad body needs to stay out of local memory; with three 8+1-warp CTAs per SM
+// at 72 registers the three drifted apart and every date ended with SMs running one CTA: 38.9 -> 33.6 ms at 1e8 x 50,
+// profiles/r2_tune_amer_chain_shapes.log). The producer's elected lane streams tiles of row m, row m-1 and the dates
+// through a 3-deep mbarrier ring with cp.async.bulk; tile k of CTA b is b + k*grid, so the sums are bit-reproducible.
+// Also measured, and not kept: a persistent all-dates kernel with an in-kernel grid barrier (slower on every size,
+// profiles/r2_tune_amer_persistent_deferred_gathers.log); tiles handed out on demand from an atomic counter (as fast as
+// the one-CTA shape, but the assignment -- hence the rounding of the sums -- changes from run to run; kept behind
+// PCF_AMER_ONDEMAND in tuning builds).
 // mom[0..7] = n_itm, Sx, Sx^2, Sx^3, Sx^4, Sy, Syx, Syx^2 with x = S - E, y = discounted cash flow; products are formed
-// exactly like the reference forms them (left to right, no FMA): only the summation order differs.
+// like the reference forms them unless kContractMoments folds the last multiplication into the sum's FMA.
 constexpr int kMomFold = 16;  // tiles (64 paths per thread) between folds of the plain running sums
 #ifdef PCF_EXACT_MOMENT_PRODUCTS
 constexpr bool kContractMoments = false;  // every moment product rounded as the reference rounds it (mc_amer.cpp:51-57)
@@ -233,6 +233,12 @@ struct SweepShape {
   static constexpr int kTile = 4 * kConsumers;  // paths per tile
 };
 constexpr int kMaxStages = 6;
+
+#ifdef PCF_TUNING
+// timing-only experiments (results are WRONG with any bit set): 1 no gathers, 2 no per-path work at all (the consumers
+// only pull the tile out of the ring), 4 no stores of exercise dates, 8 deferred gathers are issued but not waited for (tools/tune_amer_chain.py)
+__constant__ int c_sweep_knobs;
+#endif
 
 template <typename WT> struct WhenBits;
 template <> struct WhenBits<uint8_t> { static constexpr int kFlag = 0x80, kMask = 0x7f; };
@@ -309,6 +315,7 @@ template <> struct WhenQuad<uint8_t> {
     return (uint32_t)w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16) | ((uint32_t)w[3] << 24);
   }
   static __device__ __forceinline__ Vec splat(int d) { return 0x01010101u * (uint32_t)d; }
+  static __device__ __forceinline__ bool same(Vec a, Vec b) { return a == b; }
 };
 template <> struct WhenQuad<uint16_t> {
   typedef uint2 Vec;
@@ -319,6 +326,7 @@ template <> struct WhenQuad<uint16_t> {
     return make_uint2((uint32_t)w[0] | ((uint32_t)w[1] << 16), (uint32_t)w[2] | ((uint32_t)w[3] << 16));
   }
   static __device__ __forceinline__ Vec splat(int d) { return make_uint2(0x00010001u * (uint32_t)d, 0x00010001u * (uint32_t)d); }
+  static __device__ __forceinline__ bool same(Vec a, Vec b) { return a.x == b.x && a.y == b.y; }
 };
 
 // What every consumer thread needs to know about date m once its regression is solved.
@@ -367,36 +375,37 @@ __device__ __forceinline__ DateRule make_rule(int mode, const double* s_coef, do
   return R;
 }
 
-#ifdef PCF_TUNING
-// timing-only experiments (results are WRONG with any bit set): 1 no gathers, 2 no per-path work at all (the consumers
-// only pull the tile out of the ring), 4 no stores of exercise dates (tools/tune_amer_chain.py)
-__constant__ int c_sweep_knobs;
-#endif
 
-// One quad (4 consecutive paths, one 32-byte sector per row) at date m: the decision of date m on the dates w[], then
-// the terms of date m-1's moments (kMoments) or of the final sum (kFinal) added to run[] / cnt. Returns true when any of
-// the four dates changed. src = row m, sp = row m-1 (kMoments). colp + d*row_bytes is the address of paths[d][first path
-// of the quad]; s_disc[k] = exp(-r dt k), s_abs[k] = exp(-r k dt).
-template <typename WT, bool kMoments, bool kFinal>
-__device__ __forceinline__ bool sweep_quad(const double (&src)[4], const double (&sp)[4], int (&w)[4], bool live,
-                                           const DateRule& R, int m, double sgn, double nE,
-                                           const char* colp, size_t row_bytes, const double* s_disc,
-                                           const double* s_abs, double (&run)[8], int& cnt) {
+// exercise test of one path (mc_amer.cpp:97-103): returns `booked` when the path exercises at this date, else `w`
+__device__ __forceinline__ int decide_regression(double cx, const DateRule& R, int w) {
+  const double yhat = __dadd_rn(__dadd_rn(R.c0, __dmul_rn(R.c1s, cx)), __dmul_rn(R.c2, __dmul_rn(cx, cx)));
+  const double pq = __dadd_rn(cx, R.nE2);  // before the max(., 0): max(t, 0) > y <=> t > y | 0 > y
+  int out;
+  asm("{\n\t.reg .pred p, q;\n\t"
+      "setp.gt.f64 p, %1, 0d0000000000000000;\n\t"
+      "setp.neu.and.f64 p, %1, %2, p;\n\t"
+      "setp.lt.f64 q, %3, 0d0000000000000000;\n\t"
+      "setp.gt.or.f64 q, %4, %3, q;\n\t"
+      "and.pred p, p, q;\n\t"
+      "selp.s32 %0, %5, %6, p;\n\t}"
+      : "=r"(out)
+      : "d"(cx), "d"(R.sentinel), "d"(yhat), "d"(pq), "r"(R.booked), "r"(w));
+  return out;
+}
+
+// One quad (4 consecutive paths, one 32-byte sector of row 1) at the LAST step of the sweep, date m = 1: the decision of
+// date 1 on the dates w[], then the discounted cash flows (mc_amer.cpp:109-111) added to run[0] (sum) and run[1] (sum
+// of squares). Returns true when any of the four dates changed. colp + d*row_bytes is the address of paths[d][first
+// path of the quad]; s_disc[k] = exp(-r dt k), s_abs[k] = exp(-r k dt).
+template <typename WT>
+__device__ __forceinline__ bool sweep_quad_final(const double (&src)[4], int (&w)[4], const DateRule& R, int m,
+                                                 double sgn, double nE, const char* colp, size_t row_bytes,
+                                                 const double* s_disc, const double* s_abs, double (&run)[8]) {
   constexpr int kFlag = WhenBits<WT>::kFlag, kMask = WhenBits<WT>::kMask;
-  const double* s_disc_m = s_disc - (m - 1);  // s_disc_m[d] = exp(-r dt (d - (m-1)))
-  // cp*(S_m - E), cp*(S_{m-1} - E)
-  double cx[4], ex[4], gv[4];
-  bool need[4];
+  double cx[4], gv[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     cx[e] = fma(sgn, src[e], nE);  // payoff(S_m) = max(cx, 0)
-    need[e] = live;
-    ex[e] = 0.0;
-    if (kMoments) {
-      const double c = fma(sgn, sp[e], nE);
-      need[e] = live && c > 0.0;
-      ex[e] = need[e] ? c : 0.0;
-    }
     gv[e] = src[e];
   }
   // (b) decision of date m
@@ -404,13 +413,11 @@ __device__ __forceinline__ bool sweep_quad(const double (&src)[4], const double 
   if (R.mode >= 2) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const double yhat = __dadd_rn(__dadd_rn(R.c0, __dmul_rn(R.c1s, cx[e])), __dmul_rn(R.c2, __dmul_rn(cx[e], cx[e])));
-      const double pq = __dadd_rn(cx[e], R.nE2);  // before the max(., 0): max(t, 0) > y <=> t > y | 0 > y
-      const bool exer = live & (cx[e] > 0.0) & (cx[e] != R.sentinel) & ((pq > yhat) | (0.0 > yhat));
-      w[e] = exer ? R.booked : w[e];
-      changed |= exer;
+      const int wn = decide_regression(cx[e], R, w[e]);
+      changed |= wn != w[e];
+      w[e] = wn;
     }
-  } else if (R.mode == 1 && live) {
+  } else if (R.mode == 1) {
     // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against the discounted cash flow
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -426,63 +433,173 @@ __device__ __forceinline__ bool sweep_quad(const double (&src)[4], const double 
       }
     }
   }
-  // (c) gathers: the cash flow is needed (in the money at m-1, or the final sum) and the path did not exercise at m,
-  // so it comes from paths[when][n] (mc_amer.cpp:50) -- frequent under PCF_FLAG_AMER_LSM and for calls, rare for the
-  // reference rule's puts
+  // (c) the cash flow of a path that did not exercise at m comes from paths[when][n] (mc_amer.cpp:50)
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int d = w[e] & kMask;
-#ifdef PCF_TUNING
-    if (c_sweep_knobs & 1) continue;
-#endif
-    if (need[e] && d != m)
-      gv[e] = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
+    if (d != m) gv[e] = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
   }
-  // (d) moments of date m-1 / final sum. Out-of-the-money (and dead) lanes add exact zeros.
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int d = w[e] & kMask;
     const double cr = fma(sgn, gv[e], nE);
-    const double cs = (need[e] && cr > 0.0) ? cr : 0.0;  // payoff(paths[when][n]), 0 when not needed
-    if (kMoments) {
-      const double x1 = ex[e];
-      const double cont = __dmul_rn(s_disc_m[d], cs);  // d >= m: index in [1, M]
-      cnt += need[e] ? 1 : 0;
-      if (kContractMoments) {
-        // 8 FP64 instructions instead of 13: x^3, x^4, y x, y x^2 enter their sums through one FMA each (x^4 as x^2 x^2,
-        // y x^2 as y (x^2)). Each product differs from the reference's left-to-right one by at most an ulp -- the same
-        // order as the reassociation of the sums themselves, far inside the 1e-12 replay tolerance.
-        const double x2 = __dmul_rn(x1, x1);
-        run[1] += x1;
-        run[2] += x2;
-        run[3] = fma(x2, x1, run[3]);
-        run[4] = fma(x2, x2, run[4]);
-        run[5] += cont;
-        run[6] = fma(cont, x1, run[6]);
-        run[7] = fma(cont, x2, run[7]);
-      } else {
-        const double x2 = __dmul_rn(x1, x1), x3 = __dmul_rn(x2, x1), x4 = __dmul_rn(x3, x1);
-        const double yx = __dmul_rn(cont, x1), yx2 = __dmul_rn(yx, x1);
-        run[1] += x1;
-        run[2] += x2;
-        run[3] += x3;
-        run[4] += x4;
-        run[5] += cont;
-        run[6] += yx;
-        run[7] += yx2;
-      }
-    }
-    if (kFinal) {
-      // exercise_st (mc_amer.cpp:103): the regression branch booked payoff(x, E) = max(cp*(x - E), 0), x = S - E;
-      // a flagged path has cs > 0, a dead lane has w = m (no flag) and cs = 0
-      const double sq = __dadd_rn(cs, nE);
-      const double stv = (w[e] & kFlag) ? (sq > 0.0 ? sq : 0.0) : cs;
-      const double v = __dmul_rn(s_abs[d], stv);
-      run[0] += v;
-      run[1] += v * v;
-    }
+    const double cs = cr > 0.0 ? cr : 0.0;  // payoff(paths[when][n])
+    // exercise_st (mc_amer.cpp:103): the regression branch booked payoff(x, E) = max(cp*(x - E), 0), x = S - E;
+    // a flagged path has cs > 0
+    const double sq = __dadd_rn(cs, nE);
+    const double stv = (w[e] & kFlag) ? (sq > 0.0 ? sq : 0.0) : cs;
+    const double v = __dmul_rn(s_abs[d], stv);
+    run[0] += v;
+    run[1] += v * v;
   }
   return changed;
+}
+
+// ---- dates M .. 2: the lean per-quad body -------------------------------------------------------------------------
+// The reference's per-path arithmetic (mc_amer.cpp:41-59, 97-103), arranged for the instruction count: the ring alone
+// streams a date in 0.22 ms, the full kernel needs 0.47 ms, and its time follows the number of instructions issued per
+// tile (profiles/r2_tune_amer_chain_*.log):
+//   * the regressor and the cash flow are carried DOUBLED, X = c + |c| = 2 max(c, 0) and C = cr + |cr| = 2 payoff: one
+//     DADD instead of a compare and two selects. Every term of a moment is then the reference's term times an exact
+//     power of two (2 x, 4 x^2, 8 x^3, 16 x^4, 2 y, 4 y x, 8 y x^2), rounded exactly as the unscaled product is, and
+//     the sums are scaled back exactly when the CTA totals are formed;
+//   * a path out of the money at m-1 has X = 0, which zeroes its x and y x^k terms by itself; a path that exercised AT
+//     m (the common case) is one date ahead of m-1, so its discount factor is the constant exp(-r dt), no table look-up;
+//   * every tile is complete (rows are padded to a multiple of the tile with never-in-the-money columns), so there is
+//     no per-quad bounds test;
+//   * the exercise test is four FP64 compares chained through their predicate operands (inline PTX: left to itself the
+//     compiler turns max(t, 0) > y into a NaN-propagating maximum, seven instructions);
+//   * ONE gather per thread and tile is deferred: it is issued here as an asynchronous copy and its terms are added
+//     while the NEXT tile is processed (Pending), so the DRAM round trip of paths[when][n] -- 30 % of all warp stall
+//     samples in the immediate version, profiles/r2f_ncu_amer_sweep_immediate_gathers.txt -- overlaps a whole tile of
+//     work; the paths that need one are collected in a bit mask and only the first is looked at. A second gather of
+//     the same thread in the same tile (0.5 % of the tiles under the reference's rule) is consumed at once.
+struct Pending {
+  double* g;  // this thread's landing slot in shared memory for paths[when][n] (holds a finite value at all times)
+  double X;   // 2 max(cp (S_{m-1} - E), 0) of that path
+  int j;      // when - (m-1); 0: nothing pending (s_dz[0] == 0.0 zeroes the terms)
+};
+// The deferred value travels by cp.async, not by a load into a register: the fence that hands the ring slot back
+// (fence.proxy.async -> MEMBAR.ALL.CTA) waits for every outstanding LOAD of the thread, so a register gather left in
+// flight across the tile boundary stalls the slot release instead of overlapping it (measured: 38.2 ms against 33.6 ms
+// at 1e8 x 50, profiles/r2_tune_amer_chain_lean.log); asynchronous copies are only waited for by cp.async.wait_all.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ double pending_value(const Pending& pend) {
+#ifdef PCF_TUNING
+  if (!(c_sweep_knobs & 8))  // timing experiment: the deferred value is used without waiting for it
+#endif
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  return *reinterpret_cast<volatile double*>(pend.g);
+}
+
+template <bool kContract>
+__device__ __forceinline__ void x_terms(double X, double X2, double (&run)[8]) {
+  run[1] += X;
+  run[2] += X2;
+  if (kContract) {
+    run[3] = fma(X2, X, run[3]);
+    run[4] = fma(X2, X2, run[4]);
+  } else {
+    const double X3 = __dmul_rn(X2, X);
+    run[3] += X3;
+    run[4] += __dmul_rn(X3, X);
+  }
+}
+template <bool kContract>
+__device__ __forceinline__ void y_terms(double Y, double X, double X2, double (&run)[8]) {
+  run[5] += Y;
+  if (kContract) {
+    run[6] = fma(Y, X, run[6]);
+    run[7] = fma(Y, X2, run[7]);
+  } else {
+    const double YX = __dmul_rn(Y, X);
+    run[6] += YX;
+    run[7] += __dmul_rn(YX, X);
+  }
+}
+
+// s_dz[j] = exp(-r dt j) for j >= 1, s_dz[0] = 0.0; disc1 = s_dz[1]. colp + d*row_bytes is the address of
+// paths[d][first path of the quad].
+template <typename WT>
+__device__ __forceinline__ void sweep_quad_moments(const double (&src)[4], const double (&sp)[4], int (&w)[4],
+                                                   const DateRule& R, int m, double sgn, double nE, double disc1,
+                                                   const char* colp, size_t row_bytes, const double* s_dz,
+                                                   double (&run)[8], int& cnt, Pending& pend) {
+  constexpr int kMask = WhenBits<WT>::kMask;
+  // the gather deferred by the previous tile
+  {
+    const double cr = fma(sgn, pending_value(pend), nE);
+    const double Y = __dmul_rn(s_dz[pend.j], cr + fabs(cr));
+    y_terms<kContractMoments>(Y, pend.X, __dmul_rn(pend.X, pend.X), run);
+    pend.j = 0;
+  }
+  double cx[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) cx[e] = fma(sgn, src[e], nE);  // cp (S_m - E): payoff(S_m) = max(cx, 0)
+  // (b) decision of date m
+  if (R.mode >= 2) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) w[e] = decide_regression(cx[e], R, w[e]);
+  } else if (R.mode == 1) {
+    // <= 2 paths in the money (mc_amer.cpp:75-83): true payoff against the discounted cash flow
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (cx[e] > 0.0) {
+        const int d = w[e] & kMask;
+        const double g = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
+        const double pg = fma(sgn, g, nE);  // payoff(g, E, cp) = max(cp*(g - E), 0), same rounding
+        const double cont = __dmul_rn(s_dz[d - m], pg > 0.0 ? pg : 0.0);  // d > m here: never the zeroed entry 0
+        if (cx[e] > cont) w[e] = m;
+      }
+    }
+  }
+  // (c) + (d) moments of date m-1. A path in the money at m-1 (mc_amer.cpp:44) whose exercise date is m takes its cash
+  // flow from row m, one date ahead; any other date means paths[when][n] (mc_amer.cpp:50). The paths that need that
+  // gather are collected in a bit mask, not in predicates (seven predicate registers do not hold four paths' worth of
+  // conditions: the first version of this loop spent 30 instructions per tile moving predicates in and out of a GPR)
+  unsigned gm = 0;
+  double X[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const double c = fma(sgn, sp[e], nE);
+    const bool need = c > 0.0;
+    X[e] = c + fabs(c);
+    const double X2 = __dmul_rn(X[e], X[e]);
+    const bool at_m = (w[e] & kMask) == m;
+    gm |= (need && !at_m) ? (1u << e) : 0u;
+    cnt += need ? 1 : 0;
+    x_terms<kContractMoments>(X[e], X2, run);
+    const double Y = __dmul_rn(disc1, cx[e] + fabs(cx[e]));
+    y_terms<kContractMoments>((need && at_m) ? Y : 0.0, X[e], X2, run);
+  }
+#ifdef PCF_TUNING
+  if (c_sweep_knobs & 1) return;
+#endif
+  // the gathers: the first one of the thread is deferred, further ones (rare) are consumed on the spot
+  if (gm) {
+    const int esel = __ffs(gm) - 1;
+    int dsel = (esel == 0 ? w[0] : esel == 1 ? w[1] : esel == 2 ? w[2] : w[3]) & kMask;
+#ifdef PCF_TUNING
+    if (c_sweep_knobs & 16) dsel = m;  // timing experiment: the gather reads the row that has just been streamed
+#endif
+    cp_async8(pend.g, reinterpret_cast<const double*>(colp + (size_t)(unsigned)dsel * row_bytes) + esel);
+    pend.X = esel == 0 ? X[0] : esel == 1 ? X[1] : esel == 2 ? X[2] : X[3];
+    pend.j = dsel - (m - 1);
+    if (gm & (gm - 1)) {
+#pragma unroll
+      for (int e = 1; e < 4; ++e) {
+        if ((gm >> e & 1u) && e != esel) {
+          const int d = w[e] & kMask;
+          const double gv = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
+          const double cr = fma(sgn, gv, nE);
+          const double Y = __dmul_rn(s_dz[d - (m - 1)], cr + fabs(cr));
+          y_terms<kContractMoments>(Y, X[e], __dmul_rn(X[e], X[e]), run);
+        }
+      }
+    }
+  }
 }
 
 // Fold of the plain per-thread runs (<= 4 kMomFold terms each): summed over the warp in a fixed shuffle order and added
@@ -546,6 +663,7 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
   __shared__ int s_mode;
   __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages];
   __shared__ long long s_tile[kMaxStages];  // tile held by each ring slot, -1: no more tiles
+  __shared__ double s_pend[kMoments ? kSweepConsumers : 1];  // landing slots of the deferred gathers
   __shared__ double2 s_wacc[kSweepConsumers / 32][8];
   extern __shared__ __align__(128) unsigned char dyn[];
   unsigned char* ring = dyn;                                                     // stages x kStage
@@ -558,7 +676,8 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
   asm volatile("griddepcontrol.launch_dependents;");
   if (tid < (kSweepConsumers / 32) * 8) s_wacc[tid / 8][tid % 8] = make_double2(0.0, 0.0);
   for (int k = tid; k <= a.M; k += blockDim.x) {
-    s_disc[k] = c_amer_tab[kDiscFwd + k];
+    // dates M..2 index this table from 1 (a cash flow lies at least one date ahead) and read entry 0 as "no term"
+    s_disc[k] = (kMoments && k == 0) ? 0.0 : c_amer_tab[kDiscFwd + k];
     s_abs[k] = c_amer_tab[kDiscFwd + (a.M + 1) + k];
   }
   if (tid == 0) {
@@ -574,7 +693,7 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
   const int m = a.m, cp = a.cp;
   const double E = a.E;
   const long long Np = a.Np;
-  const long long ntiles = (Np + kTilePaths - 1) / kTilePaths;
+  const long long ntiles = Np / kTilePaths;  // Np is a multiple of the tile
   const double* __restrict__ paths = a.paths;
   const double* row_m = paths + (size_t)(m - 1) * Np;
   const double* row_p = paths + (size_t)(kMoments ? m - 2 : 0) * Np;
@@ -597,7 +716,7 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
       };
       auto rows = [&](int slot, long long tt) {
         const long long c0 = (a.rev ? ntiles - 1 - tt : tt) * kTilePaths;
-        const uint32_t n = (uint32_t)((Np - c0 < kTilePaths) ? (Np - c0) : kTilePaths);  // multiple of 16
+        constexpr uint32_t n = kTilePaths;  // rows are padded to whole tiles
         unsigned char* st = ring + (size_t)slot * kStage;
         s_tile[slot] = c0;
         mbar_arrive_expect_tx(&s_full[slot], n * kPerPath);
@@ -606,7 +725,7 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
       };
       auto dates = [&](int slot) {
         const long long c0 = s_tile[slot];
-        const uint32_t n = (uint32_t)((Np - c0 < kTilePaths) ? (Np - c0) : kTilePaths);
+        constexpr uint32_t n = kTilePaths;
         bulk_g2s(ring + (size_t)slot * kStage + kTilePaths * 16, when + c0, n * (uint32_t)sizeof(WT), &s_full[slot], pol_keep);
       };
       // rows do not depend on the previous date's kernel: the first tiles' rows are in flight before the wait; their
@@ -656,6 +775,12 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
 #pragma unroll
     for (int k = 0; k < 8; ++k) run[k] = 0.0;
     int cnt = 0, fold = 0;
+    const double disc1 = c_amer_tab[kDiscFwd + 1];  // exp(-r dt): one date ahead
+    Pending pend;
+    pend.g = s_pend + (kMoments ? tid : 0);
+    if (kMoments) *pend.g = E;
+    pend.X = 0.0;
+    pend.j = 0;
     const size_t row_bytes = (size_t)Np * 8;
     const char* colp0 = reinterpret_cast<const char*>(paths) + (size_t)tid * 32 - row_bytes;
     int s = 0;
@@ -669,7 +794,6 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
       mbar_wait(&s_full[s], ph);
       const long long c0t = s_tile[s];
       if (c0t < 0) break;
-      const bool live = c0t + 4 * tid < Np;
       const double2 sa = *reinterpret_cast<const double2*>(st + tid * 32);
       const double2 sb = *reinterpret_cast<const double2*>(st + tid * 32 + 16);
       double2 pa = make_double2(0.0, 0.0), pb = pa;
@@ -677,14 +801,13 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
         pa = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32);
         pb = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32 + 16);
       }
-      WVec wv = *reinterpret_cast<const WVec*>(st + kTilePaths * 16 + tid * sizeof(WVec));
+      const WVec wv = *reinterpret_cast<const WVec*>(st + kTilePaths * 16 + tid * sizeof(WVec));
       // generic-proxy reads of the slot must be ordered before the TMA engine (async proxy) refills it: without
       // this fence a deep ring at 2 CTAs/SM produced stale reads (observed as run-to-run price noise)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
       if (++s == a.stages) { s = 0; ph ^= 1; }
-      if (!live) wv = WQ::splat(m);
 #ifdef PCF_TUNING
       ++dbg_tiles;
 #endif
@@ -701,13 +824,18 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
         continue;
       }
 #endif
-      bool changed = sweep_quad<WT, kMoments, kFinal>(src, sp, w, live, R, m, sgn, nE, colp, row_bytes,
-                                                      s_disc, s_abs, run, cnt);
+      bool changed;
+      if (kMoments) {
+        sweep_quad_moments<WT>(src, sp, w, R, m, sgn, nE, disc1, colp, row_bytes, s_disc, run, cnt, pend);
+        changed = !WQ::same(WQ::pack(w), wv);
+      } else {
+        changed = sweep_quad_final<WT>(src, w, R, m, sgn, nE, colp, row_bytes, s_disc, s_abs, run);
+      }
 #ifdef PCF_TUNING
       if (c_sweep_knobs & 4) changed = false;
 #endif
       if (R.mode >= 2) {
-        if (__any_sync(0xffffffffu, changed) && live) *wp = WQ::pack(w);
+        if (__any_sync(0xffffffffu, changed)) *wp = WQ::pack(w);  // whole 128-byte lines back
       } else if (changed) {
         *wp = WQ::pack(w);
       }
@@ -715,6 +843,11 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
         fold_runs<kSums, kMoments>(run, cnt, s_wacc, tid);
         fold = 0;
       }
+    }
+    if (kMoments) {  // the last tile's deferred gather
+      const double cr = fma(sgn, pending_value(pend), nE);
+      const double Y = __dmul_rn(s_disc[pend.j], cr + fabs(cr));
+      y_terms<kContractMoments>(Y, pend.X, __dmul_rn(pend.X, pend.X), run);
     }
     fold_runs<kSums, kMoments>(run, cnt, s_wacc, tid);
 #ifdef PCF_TUNING
@@ -737,10 +870,15 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
     }
   }
   if (kMoments) {
+    // back from the doubled cx-space to the reference's x = S - E and y: exact powers of two, and odd powers of x carry
+    // the sign of cp
     const double sgn = (double)cp;
-    acc[1].hi *= sgn; acc[1].lo *= sgn;
-    acc[3].hi *= sgn; acc[3].lo *= sgn;
-    acc[6].hi *= sgn; acc[6].lo *= sgn;
+    const double f[8] = {1.0, 0.5 * sgn, 0.25, 0.125 * sgn, 0.0625, 0.5, 0.25 * sgn, 0.125};
+#pragma unroll
+    for (int k = 1; k < kSums; ++k) {
+      acc[k].hi *= f[k];
+      acc[k].lo *= f[k];
+    }
   }
   __syncthreads();
   grid_reduce<kSums>(acc, smem, a.partials, a.ticket, a.out, &link);
@@ -779,7 +917,8 @@ static int launch_sweep(Ctx& c, bool final_date, bool dependent, int grid, int s
 static inline size_t amer_when_bytes(int M) { return M <= WhenBits<uint8_t>::kMask ? 1 : 2; }
 static inline size_t amer_when_area(long long Np, int M) { return ((size_t)Np * amer_when_bytes(M) + 255) & ~(size_t)255; }
 
-constexpr int kDefaultSweepShape = 231, kDefaultSweepStages = 2;
+constexpr int kDefaultSweepShape = 231, kDefaultSweepStages = 3;
+constexpr int kSweepMaxTile = 28 * 128;  // largest tile of any launch shape (tuning builds)
 
 // Per-date chain: one launch per exercise date, each a programmatic dependent of the one before. The moments travel
 // through the NVLink mailboxes (published by the last block of date m+1's kernel, gathered by every CTA of date m's),
@@ -857,7 +996,15 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   }
   const long long H = pairs.size(), Nl = 2 * H;
   const double dt = p.T / M;
-  const long long Np = (Nl + 15) & ~15LL;  // padded row length: 128-byte rows, 16-byte date tiles (TMA granules)
+  int shape = kDefaultSweepShape, stages = kDefaultSweepStages;
+  if (const char* v = tuning_env("PCF_AMER_SHAPE")) shape = atoi(v);   // <consumer warps><CTAs per SM>
+  if (const char* v = tuning_env("PCF_AMER_SWEEP")) stages = std::max(2, std::min(kMaxStages, atoi(v)));
+  const long long tile = 128LL * (shape / 10);
+  if (tile < 128 || tile > kSweepMaxTile) {
+    set_last_error("unknown PCF_AMER_SHAPE");
+    return PCF_EINVAL;
+  }
+  const long long Np = (Nl + tile - 1) / tile * tile;  // padded row length: whole tiles of the sweep (128-byte multiples)
   char* base = (char*)c.workspace + ws_offset;
   double* paths = (double*)base;
   void* when = (void*)(paths + (size_t)M * Np);
@@ -915,16 +1062,13 @@ int run_mc_amer(Ctx& c, const pcf_params& p, Shard pairs, const double* d_replay
   }
   c.launches++;
   if (Np != Nl) {
-    amer_pad_kernel<<<1, 128, 0, c.stream>>>(paths, Nl, Np, M, p.cp);
+    amer_pad_kernel<<<(unsigned)std::min<long long>(((Np - Nl) * M + 255) / 256, 1024), 256, 0, c.stream>>>(paths, Nl, Np, M, p.cp);
     c.launches++;
   }
   PCF_CUDA(cudaGetLastError());
 
   // Backward sweep m = M .. 1 (mc_amer.cpp:23-27, 31, 109-111). The iteration of date m consumes the moments of date m
   // and produces those of date m-1 (date 1: the final sums).
-  int shape = kDefaultSweepShape, stages = kDefaultSweepStages;
-  if (const char* v = tuning_env("PCF_AMER_SHAPE")) shape = atoi(v);   // <consumer warps><CTAs per SM>
-  if (const char* v = tuning_env("PCF_AMER_SWEEP")) stages = std::max(2, std::min(kMaxStages, atoi(v)));
   switch (shape) {
 #ifdef PCF_TUNING
     case 83: return run_sweep_chain<SweepShape<8, 3>>(c, p, paths, when, Np, stages);
@@ -954,7 +1098,7 @@ extern "C" __attribute__((visibility("default"))) int pcf_debug_sweep(unsigned l
 #endif
 
 size_t amer_workspace_bytes(long long local_pairs, int M) {
-  size_t Np = (2 * (size_t)local_pairs + 15) & ~(size_t)15;
+  size_t Np = ((2 * (size_t)local_pairs + 15) & ~(size_t)15) + kSweepMaxTile;  // rows are padded to whole tiles
   // paths, exercise dates, one tile counter per date
   return (size_t)M * Np * 8 + amer_when_area((long long)Np, M) + sizeof(unsigned int) * (size_t)(M + 1) + 256;
 }

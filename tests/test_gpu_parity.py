@@ -83,7 +83,7 @@ def test_mc_amer_replay_golden(gpu, golden):
         g = gpu.mc_amer(S0, E, r, sigma, T, c["N"], c["M"], c["payoff"], replay=w)
         assert rel(g.price, c["price"]) < REPLAY_TOL, c
         # paths [+ pad] + state fill + one fused sweep kernel per date (the kernel of date 1 also forms the final sum)
-        assert g.launches == 2 + c["M"] + (1 if c["N"] % 16 else 0)  # paths, date fill, one sweep per date (+ padding)
+        assert g.launches == 2 + c["M"] + (1 if c["N"] % 2944 else 0)  # paths, date fill, one sweep per date (+ padding to whole tiles)
 
 
 def test_mc_amer_few_itm_branches(gpu):

@@ -30,27 +30,25 @@ def per_cta(tag):
           " ".join(f"{sm}:{t:.2f}" for t, sm in per[-4:]))
 
 
-VARIANTS = [("8x3 static, no PDL (round 1)", {"PCF_AMER_SHAPE": "83", "PCF_AMER_NOPDL": "1"}),
-            ("8x3 static", {"PCF_AMER_SHAPE": "83"}),
+VARIANTS = [("8x3, no PDL (round-1 shape)", {"PCF_AMER_SHAPE": "83", "PCF_AMER_NOPDL": "1"}),
+            ("8x3", {"PCF_AMER_SHAPE": "83"}),
             ("8x3 on demand", {"PCF_AMER_SHAPE": "83", "PCF_AMER_ONDEMAND": "1"}),
-            ("7x3 static", {"PCF_AMER_SHAPE": "73"}),
-            ("7x3 on demand", {"PCF_AMER_SHAPE": "73", "PCF_AMER_ONDEMAND": "1"}),
-            ("12x2 static", {"PCF_AMER_SHAPE": "122"}),
-            ("11x2 static", {"PCF_AMER_SHAPE": "112"}),
-            ("11x2 static, 3 stages", {"PCF_AMER_SHAPE": "112", "PCF_AMER_SWEEP": "3"}),
-            ("16x1 static, 3 stages", {"PCF_AMER_SHAPE": "161", "PCF_AMER_SWEEP": "3"}),
-            ("20x1 static, 2 stages", {"PCF_AMER_SHAPE": "201", "PCF_AMER_SWEEP": "2"}),
-            ("20x1 static, 3 stages", {"PCF_AMER_SHAPE": "201", "PCF_AMER_SWEEP": "3"}),
-            ("23x1 static, 2 stages", {"PCF_AMER_SHAPE": "231", "PCF_AMER_SWEEP": "2"}),
-            ("23x1 static, 3 stages", {"PCF_AMER_SHAPE": "231", "PCF_AMER_SWEEP": "3"}),
-            ("23x1 static, 4 stages", {"PCF_AMER_SHAPE": "231", "PCF_AMER_SWEEP": "4"}),
-            ("23x1 on demand, 3 stages", {"PCF_AMER_SHAPE": "231", "PCF_AMER_SWEEP": "3", "PCF_AMER_ONDEMAND": "1"}),
-            ("24x1 static, 2 stages", {"PCF_AMER_SHAPE": "241", "PCF_AMER_SWEEP": "2"}),
-            ("24x1 static, 3 stages", {"PCF_AMER_SHAPE": "241", "PCF_AMER_SWEEP": "3"}),
-            ("24x1 static, 4 stages", {"PCF_AMER_SHAPE": "241", "PCF_AMER_SWEEP": "4"}),
-            ("28x1 static, 3 stages", {"PCF_AMER_SHAPE": "281", "PCF_AMER_SWEEP": "3"}),
-            ("ENVELOPE (wrong results) 23x1 3 stages, no gathers", {"PCF_AMER_SHAPE": "231", "PCF_AMER_SWEEP": "3", "PCF_AMER_ENVELOPE": "1"}),
-            ("ENVELOPE 23x1 3 stages, ring only", {"PCF_AMER_SHAPE": "231", "PCF_AMER_SWEEP": "3", "PCF_AMER_ENVELOPE": "2"})]
+            ("7x3", {"PCF_AMER_SHAPE": "73"}),
+            ("11x2", {"PCF_AMER_SHAPE": "112"}),
+            ("11x2, 3 stages", {"PCF_AMER_SHAPE": "112", "PCF_AMER_SWEEP": "3"}),
+            ("20x1, 3 stages", {"PCF_AMER_SHAPE": "201", "PCF_AMER_SWEEP": "3"}),
+            ("23x1, 3 stages (default)", {}),
+            ("23x1, 3 stages, no PDL", {"PCF_AMER_NOPDL": "1"}),
+            ("23x1, 2 stages", {"PCF_AMER_SWEEP": "2"}),
+            ("23x1, 4 stages", {"PCF_AMER_SWEEP": "4"}),
+            ("23x1 on demand, 3 stages", {"PCF_AMER_SWEEP": "3", "PCF_AMER_ONDEMAND": "1"}),
+            ("24x1, 3 stages", {"PCF_AMER_SHAPE": "241", "PCF_AMER_SWEEP": "3"}),
+            ("ENVELOPE (wrong results) 23x1, no gathers", {"PCF_AMER_ENVELOPE": "1"}),
+            ("ENVELOPE 23x1 3 stages, no gathers", {"PCF_AMER_ENVELOPE": "1", "PCF_AMER_SWEEP": "3"}),
+            ("ENVELOPE 23x1 3 stages, gathers issued but not waited for", {"PCF_AMER_ENVELOPE": "8", "PCF_AMER_SWEEP": "3"}),
+            ("ENVELOPE 23x1 3 stages, gathers redirected to row m", {"PCF_AMER_ENVELOPE": "16", "PCF_AMER_SWEEP": "3"}),
+            ("ENVELOPE 23x1, no date stores", {"PCF_AMER_ENVELOPE": "4"}),
+            ("ENVELOPE 23x1, ring only", {"PCF_AMER_ENVELOPE": "2"})]
 KNOBS = ("PCF_AMER_SHAPE", "PCF_AMER_ONDEMAND", "PCF_AMER_NOPDL", "PCF_AMER_SWEEP", "PCF_AMER_ENVELOPE")
 for rep in range(3):
     for name, env in VARIANTS:
