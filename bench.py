@@ -67,7 +67,7 @@ WORKLOADS = {
                               exec_src="ncu: 640 FP64 + 160 IMAD.WIDE warp instructions per path"),
     "mc_amer": dict(config="mc_amer put, 1e8 paths x 50 exercise dates, paths in HBM (BASELINE config 5)",
                     N=100_000_000, M=50, steps_per_unit=50, bytes=36.0, bound="hbm", unit="path-steps/s",
-                    kernel="amer_sweep_persistent_kernel+amer_paths_kernel+amer_pad_kernel", traffic_all=True),
+                    kernel="amer_sweep_kernel+amer_paths_kernel+amer_pad_kernel+amer_fill_when_kernel", traffic_all=True),
     "binom_embar": dict(config="binom_embar call 100/100/.05/.2/1, N=1e8 steps (BASELINE config 2)",
                         N=100_000_000, M=0, steps_per_unit=1, slots=85.0, bound="fp64", unit="terms/s",
                         kernel="binom_terms_kernel"),

@@ -287,6 +287,55 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
     }
   } while (!done);
 }
+// Consumer side of the ring, on 32-bit shared-state-space addresses computed once per kernel (a generic pointer makes the
+// compiler rebuild the shared-window address -- S2UR / UMOV / LEA -- at every use inside the tile loop). The first
+// probe is inline; only a phase that is not yet complete enters the bounded loop.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  uint32_t done, spins = 0;
+  unsigned long long t0 = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (++spins & 63u) == 0u) {
+      const unsigned long long now = xchg_now_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 3ull * kXchgTimeoutNs) __trap();
+    }
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (!done) mbar_wait_slow(bar, parity);
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long lds_s64(uint32_t a) {
+  long long v;
+  asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t x) {  // keeps a loop-invariant address in its register
+  asm volatile("" : "+r"(x));
+  return x;
+}
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar`; streamed data is marked evict-first in L2
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
   asm volatile(
@@ -316,6 +365,11 @@ template <> struct WhenQuad<uint8_t> {
   }
   static __device__ __forceinline__ Vec splat(int d) { return 0x01010101u * (uint32_t)d; }
   static __device__ __forceinline__ bool same(Vec a, Vec b) { return a == b; }
+  static __device__ __forceinline__ Vec lds(uint32_t a) {
+    Vec v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+  }
 };
 template <> struct WhenQuad<uint16_t> {
   typedef uint2 Vec;
@@ -327,6 +381,11 @@ template <> struct WhenQuad<uint16_t> {
   }
   static __device__ __forceinline__ Vec splat(int d) { return make_uint2(0x00010001u * (uint32_t)d, 0x00010001u * (uint32_t)d); }
   static __device__ __forceinline__ bool same(Vec a, Vec b) { return a.x == b.x && a.y == b.y; }
+  static __device__ __forceinline__ Vec lds(uint32_t a) {
+    Vec v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+  }
 };
 
 // What every consumer thread needs to know about date m once its regression is solved.
@@ -472,26 +531,44 @@ __device__ __forceinline__ bool sweep_quad_final(const double (&src)[4], int (&w
 //   * ONE gather per thread and tile is deferred: it is issued here as an asynchronous copy and its terms are added
 //     while the NEXT tile is processed (Pending), so the DRAM round trip of paths[when][n] -- 30 % of all warp stall
 //     samples in the immediate version, profiles/r2f_ncu_amer_sweep_immediate_gathers.txt -- overlaps a whole tile of
-//     work; the paths that need one are collected in a bit mask and only the first is looked at. A second gather of
-//     the same thread in the same tile (0.5 % of the tiles under the reference's rule) is consumed at once.
+//     work; the paths that need one are collected in a bit mask. A thread's first gather of a tile keeps its regressor
+//     in registers; a second one (0.5 % of the threads, but 15-18 % of the warps have such a thread in every tile, and
+//     consuming it on the spot cost 7 % of all stall samples) goes through a small record in shared memory; a third
+//     or fourth is consumed at once.
 struct Pending {
-  double* g;  // this thread's landing slot in shared memory for paths[when][n] (holds a finite value at all times)
+  uint32_t g;  // this thread's landing slot in shared memory for paths[when][n] (holds a finite value at all times)
   double X;   // 2 max(cp (S_{m-1} - E), 0) of that path
-  int j;      // when - (m-1); 0: nothing pending (s_dz[0] == 0.0 zeroes the terms)
+  int j;      // when - (m-1); 0: nothing pending (s_dz[0] == 0.0 zeroes the terms); kSecond: see g2
+  uint32_t g2;  // a thread's SECOND gather of a tile (15 % of the warps have such a thread in every tile): a 24-byte
+                // record in shared memory -- the value (asynchronous copy), X and the table index -- consumed with the
+                // first one; kept out of the registers because it is rare
 };
+constexpr int kSecond = 1 << 20;
 // The deferred value travels by cp.async, not by a load into a register: the fence that hands the ring slot back
 // (fence.proxy.async -> MEMBAR.ALL.CTA) waits for every outstanding LOAD of the thread, so a register gather left in
 // flight across the tile boundary stalls the slot release instead of overlapping it (measured: 38.2 ms against 33.6 ms
 // at 1e8 x 50, profiles/r2_tune_amer_chain_lean.log); asynchronous copies are only waited for by cp.async.wait_all.
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ double pending_value(const Pending& pend) {
 #ifdef PCF_TUNING
   if (!(c_sweep_knobs & 8))  // timing experiment: the deferred value is used without waiting for it
 #endif
   asm volatile("cp.async.wait_all;" ::: "memory");
-  return *reinterpret_cast<volatile double*>(pend.g);
+  return lds_f64(pend.g);
 }
 
 template <bool kContract>
@@ -520,21 +597,30 @@ __device__ __forceinline__ void y_terms(double Y, double X, double X2, double (&
   }
 }
 
+// The terms of the gathers a thread deferred in the previous tile (all lanes of the warp call it)
+__device__ __forceinline__ void consume_pending(Pending& pend, double sgn, double nE, uint32_t s_dz, double (&run)[8]) {
+  const double cr = fma(sgn, pending_value(pend), nE);
+  const double Y = __dmul_rn(lds_f64(s_dz + 8u * (uint32_t)(pend.j & (kSecond - 1))), cr + fabs(cr));
+  y_terms<kContractMoments>(Y, pend.X, __dmul_rn(pend.X, pend.X), run);
+  if (__any_sync(0xffffffffu, pend.j & kSecond)) {
+    if (pend.j & kSecond) {
+      const double cr2 = fma(sgn, lds_f64(pend.g2), nE);
+      const double X2 = lds_f64(pend.g2 + 8u);
+      const double Y2 = __dmul_rn(lds_f64(s_dz + 8u * lds_u32(pend.g2 + 16u)), cr2 + fabs(cr2));
+      y_terms<kContractMoments>(Y2, X2, __dmul_rn(X2, X2), run);
+    }
+  }
+  pend.j = 0;
+}
+
 // s_dz[j] = exp(-r dt j) for j >= 1, s_dz[0] = 0.0; disc1 = s_dz[1]. colp + d*row_bytes is the address of
 // paths[d][first path of the quad].
 template <typename WT>
 __device__ __forceinline__ void sweep_quad_moments(const double (&src)[4], const double (&sp)[4], int (&w)[4],
                                                    const DateRule& R, int m, double sgn, double nE, double disc1,
-                                                   const char* colp, size_t row_bytes, const double* s_dz,
+                                                   const char* colp, size_t row_bytes, uint32_t s_dz,
                                                    double (&run)[8], int& cnt, Pending& pend) {
   constexpr int kMask = WhenBits<WT>::kMask;
-  // the gather deferred by the previous tile
-  {
-    const double cr = fma(sgn, pending_value(pend), nE);
-    const double Y = __dmul_rn(s_dz[pend.j], cr + fabs(cr));
-    y_terms<kContractMoments>(Y, pend.X, __dmul_rn(pend.X, pend.X), run);
-    pend.j = 0;
-  }
   double cx[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) cx[e] = fma(sgn, src[e], nE);  // cp (S_m - E): payoff(S_m) = max(cx, 0)
@@ -550,7 +636,7 @@ __device__ __forceinline__ void sweep_quad_moments(const double (&src)[4], const
         const int d = w[e] & kMask;
         const double g = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
         const double pg = fma(sgn, g, nE);  // payoff(g, E, cp) = max(cp*(g - E), 0), same rounding
-        const double cont = __dmul_rn(s_dz[d - m], pg > 0.0 ? pg : 0.0);  // d > m here: never the zeroed entry 0
+        const double cont = __dmul_rn(lds_f64(s_dz + 8u * (uint32_t)(d - m)), pg > 0.0 ? pg : 0.0);  // d > m: never entry 0
         if (cx[e] > cont) w[e] = m;
       }
     }
@@ -574,6 +660,8 @@ __device__ __forceinline__ void sweep_quad_moments(const double (&src)[4], const
     const double Y = __dmul_rn(disc1, cx[e] + fabs(cx[e]));
     y_terms<kContractMoments>((need && at_m) ? Y : 0.0, X[e], X2, run);
   }
+  // the gathers deferred by the previous tile: consumed as late as possible, a whole tile's work after their issue
+  consume_pending(pend, sgn, nE, s_dz, run);
 #ifdef PCF_TUNING
   if (c_sweep_knobs & 1) return;
 #endif
@@ -587,14 +675,23 @@ __device__ __forceinline__ void sweep_quad_moments(const double (&src)[4], const
     cp_async8(pend.g, reinterpret_cast<const double*>(colp + (size_t)(unsigned)dsel * row_bytes) + esel);
     pend.X = esel == 0 ? X[0] : esel == 1 ? X[1] : esel == 2 ? X[2] : X[3];
     pend.j = dsel - (m - 1);
-    if (gm & (gm - 1)) {
+    unsigned rest = gm & (gm - 1);
+    if (rest) {
+      // second gather: deferred through the record; third and fourth (vanishingly rare) consumed on the spot
+      const int e2 = __ffs(rest) - 1;  // 1..3
+      const int d2 = (e2 == 1 ? w[1] : e2 == 2 ? w[2] : w[3]) & kMask;
+      cp_async8(pend.g2, reinterpret_cast<const double*>(colp + (size_t)(unsigned)d2 * row_bytes) + e2);
+      sts_f64(pend.g2 + 8u, e2 == 1 ? X[1] : e2 == 2 ? X[2] : X[3]);
+      sts_u32(pend.g2 + 16u, (uint32_t)(d2 - (m - 1)));
+      pend.j |= kSecond;
+      rest &= rest - 1;
 #pragma unroll
-      for (int e = 1; e < 4; ++e) {
-        if ((gm >> e & 1u) && e != esel) {
+      for (int e = 2; e < 4; ++e) {
+        if (rest >> e & 1u) {
           const int d = w[e] & kMask;
           const double gv = __ldg(reinterpret_cast<const double*>(colp + (size_t)(unsigned)d * row_bytes) + e);
           const double cr = fma(sgn, gv, nE);
-          const double Y = __dmul_rn(s_dz[d - (m - 1)], cr + fabs(cr));
+          const double Y = __dmul_rn(lds_f64(s_dz + 8u * (uint32_t)(d - (m - 1))), cr + fabs(cr));
           y_terms<kContractMoments>(Y, X[e], __dmul_rn(X[e], X[e]), run);
         }
       }
@@ -663,7 +760,8 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
   __shared__ int s_mode;
   __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages];
   __shared__ long long s_tile[kMaxStages];  // tile held by each ring slot, -1: no more tiles
-  __shared__ double s_pend[kMoments ? kSweepConsumers : 1];  // landing slots of the deferred gathers
+  __shared__ double s_pend[kMoments ? kSweepConsumers : 1];      // landing slots of the deferred gathers
+  __shared__ double s_pend2[kMoments ? 3 * kSweepConsumers : 1];  // records of the second deferred gather of a thread
   __shared__ double2 s_wacc[kSweepConsumers / 32][8];
   extern __shared__ __align__(128) unsigned char dyn[];
   unsigned char* ring = dyn;                                                     // stages x kStage
@@ -777,36 +875,43 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
     int cnt = 0, fold = 0;
     const double disc1 = c_amer_tab[kDiscFwd + 1];  // exp(-r dt): one date ahead
     Pending pend;
-    pend.g = s_pend + (kMoments ? tid : 0);
-    if (kMoments) *pend.g = E;
+    pend.g = smem_u32(s_pend + (kMoments ? tid : 0));
+    pend.g2 = smem_u32(s_pend2 + (kMoments ? 3 * tid : 0));
+    if (kMoments) s_pend[tid] = E;
     pend.X = 0.0;
     pend.j = 0;
     const size_t row_bytes = (size_t)Np * 8;
     const char* colp0 = reinterpret_cast<const char*>(paths) + (size_t)tid * 32 - row_bytes;
     int s = 0;
     uint32_t ph = 0;
+    const uint32_t full0 = opaque(smem_u32(&s_full[0])), empty0 = opaque(smem_u32(&s_empty[0]));
+    const uint32_t tile0 = opaque(smem_u32(&s_tile[0])), dz0 = opaque(smem_u32(s_disc));
+    pend.g = opaque(pend.g);
+    pend.g2 = opaque(pend.g2);
+    const uint32_t quad0 = opaque(smem_u32(ring) + (uint32_t)tid * 32u);          // this thread's sector of slot 0, row m
+    const uint32_t date0 = opaque(smem_u32(ring) + (uint32_t)kTilePaths * 16u + (uint32_t)tid * (uint32_t)sizeof(WVec));
 #ifdef PCF_TUNING
     const long long dbg_t0 = clock64();
     int dbg_tiles = 0;
 #endif
     for (;;) {
-      const unsigned char* st = ring + (size_t)s * kStage;
-      mbar_wait(&s_full[s], ph);
-      const long long c0t = s_tile[s];
+      mbar_wait_addr(full0 + 8u * (uint32_t)s, ph);
+      const long long c0t = lds_s64(tile0 + 8u * (uint32_t)s);
       if (c0t < 0) break;
-      const double2 sa = *reinterpret_cast<const double2*>(st + tid * 32);
-      const double2 sb = *reinterpret_cast<const double2*>(st + tid * 32 + 16);
+      const uint32_t so = (uint32_t)s * (uint32_t)kStage;
+      const double2 sa = lds_f64x2(quad0 + so);
+      const double2 sb = lds_f64x2(quad0 + so + 16u);
       double2 pa = make_double2(0.0, 0.0), pb = pa;
       if (kMoments) {
-        pa = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32);
-        pb = *reinterpret_cast<const double2*>(st + kTilePaths * 8 + tid * 32 + 16);
+        pa = lds_f64x2(quad0 + so + (uint32_t)kTilePaths * 8u);
+        pb = lds_f64x2(quad0 + so + (uint32_t)kTilePaths * 8u + 16u);
       }
-      const WVec wv = *reinterpret_cast<const WVec*>(st + kTilePaths * 16 + tid * sizeof(WVec));
+      const WVec wv = WQ::lds(date0 + so);
       // generic-proxy reads of the slot must be ordered before the TMA engine (async proxy) refills it: without
       // this fence a deep ring at 2 CTAs/SM produced stale reads (observed as run-to-run price noise)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);
+      if ((tid & 31) == 0) mbar_arrive_addr(empty0 + 8u * (uint32_t)s);
       if (++s == a.stages) { s = 0; ph ^= 1; }
 #ifdef PCF_TUNING
       ++dbg_tiles;
@@ -826,7 +931,7 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
 #endif
       bool changed;
       if (kMoments) {
-        sweep_quad_moments<WT>(src, sp, w, R, m, sgn, nE, disc1, colp, row_bytes, s_disc, run, cnt, pend);
+        sweep_quad_moments<WT>(src, sp, w, R, m, sgn, nE, disc1, colp, row_bytes, dz0, run, cnt, pend);
         changed = !WQ::same(WQ::pack(w), wv);
       } else {
         changed = sweep_quad_final<WT>(src, w, R, m, sgn, nE, colp, row_bytes, s_disc, s_abs, run);
@@ -844,11 +949,7 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
         fold = 0;
       }
     }
-    if (kMoments) {  // the last tile's deferred gather
-      const double cr = fma(sgn, pending_value(pend), nE);
-      const double Y = __dmul_rn(s_disc[pend.j], cr + fabs(cr));
-      y_terms<kContractMoments>(Y, pend.X, __dmul_rn(pend.X, pend.X), run);
-    }
+    if (kMoments) consume_pending(pend, sgn, nE, dz0, run);  // the last tile's deferred gathers
     fold_runs<kSums, kMoments>(run, cnt, s_wacc, tid);
 #ifdef PCF_TUNING
     if (tid == 0 && a.dbg) {
