@@ -393,6 +393,35 @@ def ncu_traffic(kernel_names, all_kernels=False):
     return sum(v["dram_bytes_per_launch"] * v["launches"] for v in hits) / steps
 
 
+_NCU_DIGEST = {"mc_asia": "mc_asia", "mc_eur": "mc_eur", "mc_eur_stated": "mc_eur", "mc_eur_multi": "basket_equi",
+               "mc_basket_general": "basket_general", "mc_amer": "amer_sweep", "binom_embar": "binom_screen",
+               "binom_embar_max": "binom_screen", "binom_embar_noscreen": "binom_noscreen", "binom_vanilla_amer": "tree_amer"}
+
+
+def ncu_counters(name):
+    """The counters BASELINE.json's north_star names, from the committed `ncu --set full` capture of the workload's
+    dominant kernel as shipped (profiles/r2g_ncu_<kernel>.txt, digested by tools/ncu_summary.py): FP64-pipe and
+    issue-slot utilisation, DRAM throughput. Static evidence (a capture, not this run); None when there is no digest."""
+    key = _NCU_DIGEST.get(name)
+    path = os.path.join(ROOT, "profiles", f"r2g_ncu_{key}.txt") if key else None
+    if not path or not os.path.exists(path):
+        return None
+    want = {"sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_pct",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_pct",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct"}
+    out = {}
+    for line in open(path):
+        parts = line.split()
+        if len(parts) >= 4 and parts[0] in want and want[parts[0]] not in out:
+            try:
+                out[want[parts[0]]] = round(float(parts[-1]), 2)
+            except ValueError:
+                pass
+    if out:
+        out["source"] = f"profiles/r2g_ncu_{key}.txt"
+    return out or None
+
+
 def binom_executed_slots(N):
     """FP64 instructions per term the binomial kernel EXECUTES with its screening pass on: every pair costs
     the two-logarithm screen (32), and only pairs with a term whose log-weight is above the -712 underflow rule go on to the
@@ -411,10 +440,18 @@ def roofline_for(name, units_per_s, fp64_dfma_per_s, hbm_bytes_per_s, hbm_src):
     w = WORKLOADS[name]
     if "exec_cycles" in w:
         # The algorithmic slot count (libdevice-based) is above what this build executes, so `frac` can exceed
-        # 1. This is the same rate against the work the kernel actually issues: FP64 instructions take 2 pipe cycles per
-        # warp, IMAD.WIDE (Philox) 4 on the same pipe (tests/ubench); the pipe offers 2 x dfma_peak / 32 cycles per second.
+        # 1. This is the same rate against a MODEL of the work the kernel issues: an FP64 instruction holds the FP64 pipe
+        # for 2 cycles per warp, a Philox IMAD.WIDE holds the fmaheavy pipe for 4 (ncu counters of tools/ubench,
+        # profiles/r2g_ncu_ubench_pipes.txt), and a loop that mixes the two runs at 0.85-0.87 of the SUM of both, far
+        # from their maximum (same file: 137 us DFMA alone, 287 us IMAD.WIDE alone, 369 us mixed), so the budget per unit
+        # is taken as 2 #FP64 + 4 #IMAD.WIDE cycles. It is a model, not a counter: the ncu counters of the shipped kernel
+        # are in `ncu` below.
         r["executed_pipe_frac"] = units_per_s * w["exec_cycles"] / (2.0 * fp64_dfma_per_s)
-        r["executed_work"] = f"{w['exec_cycles']:g} FP64-pipe cycles per warp and unit ({w['exec_src']})"
+        r["executed_work"] = (f"{w['exec_cycles']:g} cycles per warp and unit in the additive FP64 + IMAD.WIDE model "
+                              f"({w['exec_src']})")
+    nc = ncu_counters(name)
+    if nc:
+        r["ncu"] = nc
     if name.startswith("binom_embar") and name != "binom_embar_noscreen":
         # the screening pass settles most pairs with ~32 FP64 instructions, so the ALGORITHMIC 85 slots per term (which the
         # unscreened entry is quoted on) overstate what this run executed: report the rate against executed work and mark

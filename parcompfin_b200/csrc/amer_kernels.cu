@@ -1065,7 +1065,7 @@ static int run_sweep_chain(Ctx& c, const pcf_params& p, const double* paths, voi
 #ifdef PCF_TUNING
     sa.dbg = (m == dbg_date && grid <= 1024) ? g_sweep_dbg : nullptr;
 #endif
-    if (m < M) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));  // no-op unless this is the NCCL path
+    if (m < M && nccl_path) PCF_TRY(allreduce_sum(c, mom[m & 1], 8));
     sa.out = (m > 1) ? mom[(m - 1) & 1] : final_out(c);
     PeerLink l = c.link;
     l.host_err = c.perr_dev;
