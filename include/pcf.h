@@ -109,7 +109,9 @@ typedef struct pcf_result {
 /* --- lifetime --------------------------------------------------------------------------------- */
 /* Single process driving the first `gpus` visible devices (0 = all): the front ends' trailing
  * [gpus] argument, mirroring the [threads] argument of the reference's _omp programs
- * (src/mc_eur_omp.cpp:41). Builds an NCCL communicator across them when gpus > 1. */
+ * (src/mc_eur_omp.cpp:41). gpus > visible devices is PCF_EINVAL. With gpus > 1 the GPUs exchange their partial
+ * moments through NVLink peer-memory mailboxes (csrc/xchg.cuh); an NCCL communicator is built only when peer access
+ * is unavailable or PCF_NO_PEER is set, or later by pcf_peer_enable(0). */
 PCF_API int pcf_init(int gpus);
 /* One process per GPU (torchrun / mpirun style). `nccl_id` is the 128-byte NCCL unique id created
  * by rank 0 with pcf_nccl_unique_id() and distributed by the caller (any transport); may be NULL

@@ -18,10 +18,14 @@
 namespace pcf {
 
 constexpr int kBinomBlock = 256;
+// profiles/r2_tune_binom_ways.log: with the screen four pairs side by side at 2 CTAs/SM (3.40 -> 3.00 ms at N = 2^31-1);
+// without it the full routine wants occupancy, one pair at 3 CTAs/SM
+constexpr int kDefaultBinomScreened = 42, kDefaultBinomUnscreened = 13;
 
-__global__ void __launch_bounds__(kBinomBlock, 4) binom_terms_kernel(BinomArgs a, const MathTables* __restrict__ tables,
-                                                                  PeerLink link, double* partials,
-                                                                  unsigned int* ticket, double* out) {
+template <int kScreenWays, int kMinBlocks>
+__global__ void __launch_bounds__(kBinomBlock, kMinBlocks) binom_terms_kernel(BinomArgs a, const MathTables* __restrict__ tables,
+                                                                           PeerLink link, double* partials,
+                                                                           unsigned int* ticket, double* out) {
   __shared__ double smem[1 * 2 * 32];
   extern __shared__ __align__(16) unsigned char tab_smem[];
   const TableView tv = stage_tables(tables, tab_smem);
@@ -40,6 +44,17 @@ __global__ void __launch_bounds__(kBinomBlock, 4) binom_terms_kernel(BinomArgs a
     // the loop carries x and N-x as doubles (exact below 2^53): no 64-bit integer conversions per pair
     double x = (double)i, nx = (double)(a.N - i);
     const double step = (double)T;
+    // kScreenWays pairs are screened side by side: their logarithms are independent chains, and one pair per iteration
+    // left the FP64 pipe waiting on its own results ("wait" was 25 % of the stall samples, profiles/r2g_ncu_binom_screen.txt).
+    // The pairs that survive are still added in the order i, i+T, ...: the sum is bit-identical.
+    for (; i + (kScreenWays - 1) * T < a.i1; i += kScreenWays * T, x += kScreenWays * step, nx -= kScreenWays * step) {
+      bool dead[kScreenWays];
+#pragma unroll
+      for (int k = 0; k < kScreenWays; ++k) dead[k] = pair_dead(x + k * step, nx - k * step, a, tv, hc);
+#pragma unroll
+      for (int k = 0; k < kScreenWays; ++k)
+        if (!dead[k]) acc.add(pair_terms(i + k * T, a, tv, hc));
+    }
     for (; i < a.i1; i += T, x += step, nx -= step) {
       if (pair_dead(x, nx, a, tv, hc)) continue;  // both weights underflow: the pair adds exactly 0.0
       acc.add(pair_terms(i, a, tv, hc));
@@ -67,9 +82,31 @@ int run_binom(Ctx& c, const pcf_params& p, Shard pairs, bool add_mid, const Peer
   fill_binom_args(p.S0, p.E, p.r, p.sigma, p.T, p.N, p.cp, a);
   a.i0 = pairs.begin; a.i1 = pairs.end; a.add_mid = add_mid ? 1 : 0;
   a.screen = (p.flags & PCF_FLAG_BINOM_NOSCREEN) ? 0 : 1;
-  int grid = grid_for(c, pairs.size(), kBinomBlock, 4);
-  binom_terms_kernel<<<grid, kBinomBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, c.d_ticket,
-                                                                      final_out(c));
+  // launch shape: <pairs screened side by side><CTAs per SM> (PCF_BINOM_VARIANT in PCF_TUNING builds)
+  const char* v = tuning_env("PCF_BINOM_VARIANT");
+  const int variant = v ? atoi(v) : (a.screen ? kDefaultBinomScreened : kDefaultBinomUnscreened);
+#define PCF_BINOM_CASE(W, B)                                                                                  \
+  case W * 10 + B: {                                                                                          \
+    const int grid = grid_for(c, pairs.size(), kBinomBlock, B);                                               \
+    binom_terms_kernel<W, B><<<grid, kBinomBlock, kTableSmemBytes, c.stream>>>(a, c.d_tables, link, c.d_partials, \
+                                                                             c.d_ticket, final_out(c));       \
+  } break;
+  switch (variant) {
+#ifdef PCF_TUNING
+    PCF_BINOM_CASE(1, 4)
+    PCF_BINOM_CASE(2, 4)
+    PCF_BINOM_CASE(2, 3)
+    PCF_BINOM_CASE(4, 3)
+    PCF_BINOM_CASE(4, 4)
+    PCF_BINOM_CASE(8, 2)
+#endif
+    PCF_BINOM_CASE(4, 2)
+    PCF_BINOM_CASE(1, 3)
+    default:
+      set_last_error("unknown PCF_BINOM_VARIANT");
+      return PCF_EINVAL;
+  }
+#undef PCF_BINOM_CASE
   c.launches++;
   PCF_CUDA(cudaGetLastError());
   return PCF_OK;
