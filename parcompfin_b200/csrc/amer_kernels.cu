@@ -804,10 +804,11 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
       asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
       constexpr uint32_t kPerPath = 8 + (kMoments ? 8 : 0) + sizeof(WT);
-      // The first tile of a CTA is its block index; the others come off the date's counter as ring slots free up, so a
-      // CTA on a slow SM simply takes fewer of them (with a fixed b + k*grid assignment every date waits for the slowest
-      // SM: the per-CTA tile-loop times of one date spread by ~15 %, profiles/r2_tune_amer_chain.log). The next index
-      // is requested one tile ahead, so the atomic's round trip hides behind the wait for the slot.
+      // Tile k of CTA b is b + k*grid (shipped): a fixed assignment, hence bit-reproducible sums. With a.tile_ctr set
+      // (PCF_AMER_ONDEMAND, tuning builds) the tiles after the first come off the date's atomic counter as ring slots
+      // free up, requested one tile ahead so that the atomic's round trip hides behind the wait for the slot -- that
+      // balances CTAs that drift apart on one SM (profiles/r2_tune_amer_chain_on_demand_pdl_envelope.log), which the
+      // one-CTA-per-SM shape does not need.
       long long cur = blockIdx.x;
       auto next_tile = [&](long long prev) -> long long {
         return a.tile_ctr ? (long long)gridDim.x + (long long)atomicAdd(a.tile_ctr, 1u) : prev + (long long)gridDim.x;
@@ -1032,7 +1033,8 @@ static int run_sweep_chain(Ctx& c, const pcf_params& p, const double* paths, voi
   const bool nccl_path = c.world > 1 && !use_peer(c);
   const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)c.sm_count * Shape::kCtas));
   unsigned int* tile_ctr = reinterpret_cast<unsigned int*>((char*)when + amer_when_area(Np, M));
-  PCF_CUDA(cudaMemsetAsync(tile_ctr, 0, sizeof(unsigned int) * (size_t)(M + 1), c.stream));
+  const bool dynamic_tiles = tuning_env("PCF_AMER_ONDEMAND") != nullptr;  // tuning builds only (not reproducible bit for bit)
+  if (dynamic_tiles) PCF_CUDA(cudaMemsetAsync(tile_ctr, 0, sizeof(unsigned int) * (size_t)(M + 1), c.stream));
   {
     const int fg = grid_for(c, Np, 256, 8);
     if (w8) amer_fill_when_kernel<uint8_t><<<fg, 256, 0, c.stream>>>((uint8_t*)when, Np, M);
@@ -1045,7 +1047,6 @@ static int run_sweep_chain(Ctx& c, const pcf_params& p, const double* paths, voi
   sa.stages = stages;
   sa.partials = c.d_partials; sa.ticket = c.d_ticket; sa.err_flag = c.flag_dev;
   sa.dbg = nullptr;
-  const bool dynamic_tiles = tuning_env("PCF_AMER_ONDEMAND") != nullptr;
   const bool pdl = !nccl_path && tuning_env("PCF_AMER_NOPDL") == nullptr;
 #ifdef PCF_TUNING
   {

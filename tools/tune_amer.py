@@ -1,4 +1,5 @@
-"""Dev tool: sweep the launch shapes of the American kernels (PCF_AMER_GEN, PCF_AMER_SWEEP)."""
+"""Dev tool: sweep the launch shapes of the American path kernel (PCF_AMER_GEN) and the ring depth of the sweep
+(PCF_AMER_SWEEP=<stages>); the sweep shapes themselves are in tools/tune_amer_chain.py."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import parcompfin_b200 as pcf
