@@ -660,7 +660,9 @@ __device__ __forceinline__ void sweep_quad_moments(const double (&src)[4], const
     const double Y = __dmul_rn(disc1, cx[e] + fabs(cx[e]));
     y_terms<kContractMoments>((need && at_m) ? Y : 0.0, X[e], X2, run);
   }
-  // the gathers deferred by the previous tile: consumed as late as possible, a whole tile's work after their issue
+  // the gathers deferred by the previous tile, placed after this tile's moments (measured 1.5 % faster than at the top
+  // of the tile; ptxas still schedules the wait itself -- DEPBAR has no register operand -- right after the decision, so
+  // the copies get the ring wait, the slot hand-over and the decision of this tile to land, not the whole tile)
   consume_pending(pend, sgn, nE, s_dz, run);
 #ifdef PCF_TUNING
   if (c_sweep_knobs & 1) return;
