@@ -6,7 +6,8 @@
 //   * pcf_init_rank(rank, world, device, id): one process per GPU (torchrun), NCCL communicator
 //     bootstrapped from a caller-distributed unique id.
 // In both, units (paths / antithetic pairs / term pairs) are split into contiguous global index
-// ranges and the partial moments meet in one ncclAllReduce on the compute stream
+// ranges and the partial moments meet in one small all-reduce: P2P stores into NVLink-mapped mailboxes issued by the
+// reducing kernel itself (csrc/xchg.cuh), or one ncclAllReduce on the compute stream where peer access is unavailable
 // (replaces MPI_Reduce, reference src/mc_eur_mpi.cpp:36 etc.).
 // NCCL is bound lazily through dlopen("libnccl.so.2") so that single-GPU use has no NCCL
 // dependency and a host process that already carries NCCL (PyTorch) shares its copy.
@@ -899,16 +900,6 @@ int pcf_philox4x32_10(const unsigned int ctr[4], const unsigned int key[2], unsi
   return PCF_OK;
 }
 
-#ifdef PCF_TUNING
-// Tuning builds only (not declared in include/pcf.h): the 8 cycle counters the persistent sweep kernel leaves behind.
-__attribute__((visibility("default"))) int pcf_debug_counters(unsigned long long out[8]) {
-  if (g_ctx.empty()) return PCF_ENOINIT;
-  Ctx& c = g_ctx[0];
-  PCF_CUDA(cudaSetDevice(c.device));
-  PCF_CUDA(cudaMemcpy(out, c.d_out + 24, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  return PCF_OK;
-}
-#endif
 
 int pcf_fp64_peak(double seconds_target, double* dfma_per_sec) {
   if (g_ctx.empty()) return PCF_ENOINIT;

@@ -47,8 +47,8 @@ __device__ __forceinline__ unsigned long long xchg_now_ns() {
   return t;
 }
 
-// The exchange functions take the sequence number separately so that a kernel which walks many exchanges (the
-// persistent American sweep) can use its PeerLink parameter in place.
+// The exchange functions take the sequence number separately: the American sweep kernel of date m publishes exchange
+// `seq` and gathers exchange `seq - 1` with one PeerLink parameter.
 __device__ __forceinline__ bool xchg_poisoned(const PeerLink& L, unsigned long long seq) {
   Mailbox* me = L.peer[L.rank];
   const unsigned long long lo = *(volatile unsigned long long*)&me->poison_lo;
