@@ -526,6 +526,14 @@ def test_error_behaviour(gpu):
         gpu.mc_eur(*P1, 100, "call", replay=np.zeros(50))      # replay stream too short
     with pytest.raises(ValueError):
         gpu.mc_eur(*P1, 0, "call")
+    # the limits INTEGRATION.md lists (the reference takes any int): refused, never truncated
+    with pytest.raises(ValueError):
+        gpu.mc_amer(*P1, 1000, 2049, "put")                    # exercise dates beyond the discount tables
+    assert gpu.mc_amer(*P1, 64, 2048, "put", seed=1).price > 0    # the last M that is accepted (uint16 dates)
+    with pytest.raises(ValueError):
+        gpu.binom_vanilla_amer(*P1, 10_000_001, "put")         # O(N^2) tree beyond the documented cap
+    with pytest.raises(ValueError):
+        gpu.binom(*P1, 2 ** 31, "call")                        # the reference's int N
     # parameter sets that would drive exp() out of its finite range (the reference prints inf / NaN there) are refused,
     # not priced wrongly: sigma = 90 puts |x| up to 90*8.5 in play; so does a replayed "normal" of 1e6
     for fn, extra in ((gpu.mc_eur, ()), (gpu.mc_asia, (1,)), (gpu.mc_amer, (1,))):

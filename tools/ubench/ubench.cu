@@ -116,7 +116,8 @@ __global__ void k_mixed(double a, double b, uint32_t ia, double* out, long long*
 }
 
 // generic mixed kernel: CH const-operand DFMA chains + CI chains of integer op kind K
-// K: 0 = IMAD.WIDE(+use both halves via LOP3), 1 = IMAD lo only, 2 = IMAD.HI only, 3 = LOP3 only, 4 = FFMA, 5 = SHF
+// K: 0 = IMAD.WIDE(+use both halves via LOP3), 1 = IMAD lo only, 2 = IMAD.HI only, 3 = LOP3 only, 4 = FFMA, 5 = SHF,
+// 6 = IMAD.HI + IMAD lo as two instructions
 template <int CH, int CI, int K>
 __global__ void k_mix2(uint32_t ia, double* out, long long* cyc) {
   double x[CH + 1];
@@ -137,6 +138,12 @@ __global__ void k_mix2(uint32_t ia, double* out, long long* cyc) {
       if (K == 3) u[i] = (u[i] ^ y) | (u[i] & 0x55555555u) + 0;
       if (K == 4) f[i] = fmaf(f[i], f[i], 1e-3f);
       if (K == 5) u[i] = __funnelshift_l(u[i], y, 7) ^ y;
+      if (K == 6) {  // the same 64-bit product as K == 0 from IMAD.HI + IMAD (lo) issued separately
+        uint32_t hi, lo;
+        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(u[i]), "r"(0xD2511F53u));
+        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(u[i]), "r"(0xD2511F53u));
+        u[i] = hi + lo;
+      }
     }
   }
   long long t1 = clock64();
@@ -180,5 +187,6 @@ int main() {
   RUN_X(4, 0, 0, 1024);
   RUN_X(4, 4, 0, 1024); RUN_X(4, 4, 1, 1024); RUN_X(4, 4, 2, 1024); RUN_X(4, 4, 3, 1024); RUN_X(4, 4, 4, 1024); RUN_X(4, 4, 5, 1024);
   RUN_X(4, 8, 3, 1024); RUN_X(4, 8, 4, 1024); RUN_X(4, 2, 0, 1024);
+  RUN_X(0, 4, 6, 1024); RUN_X(4, 4, 6, 1024); RUN_X(4, 2, 6, 1024); RUN_X(8, 2, 0, 1024); RUN_X(8, 2, 6, 1024); RUN_X(8, 2, 2, 1024);
   return 0;
 }
