@@ -43,3 +43,19 @@ def test_bench_reads_the_committed_traffic_file():
     t = bench.ncu_traffic("amer_sweep_kernel+amer_paths_kernel")
     assert t is not None and t > 1e9          # the path kernel writes ~40 GB per launch
     assert bench.ncu_traffic("no_such_kernel") is None
+
+
+def test_bench_reads_the_committed_ncu_digests():
+    """`roofline.ncu` of every bench line comes from profiles/r2g_ncu_<kernel>.txt (tools/ncu_summary.py output)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for name in bench._NCU_DIGEST:
+        assert name in bench.WORKLOADS, name
+        c = bench.ncu_counters(name)
+        assert c is not None and os.path.exists(os.path.join(ROOT, c["source"])), name
+        assert 0.0 < c["fp64_pipe_pct"] <= 100.0 and 0.0 < c["issue_slots_pct"] <= 100.0, (name, c)
+    assert bench.ncu_counters("mc_amer")["dram_throughput_pct"] > 50.0   # the one HBM-bound line
+    assert bench.ncu_counters("no_such_workload") is None
+    # the step traffic of mc_amer: four kernels, ~157 GB per step at 1e8 x 50
+    t = bench.ncu_traffic(bench.WORKLOADS["mc_amer"]["kernel"], all_kernels=True)
+    assert 1.4e11 < t < 1.8e11
