@@ -978,28 +978,69 @@ __global__ void __launch_bounds__(Shape::kBlock, Shape::kCtas) amer_sweep_kernel
     }
 #endif
   }
-  // warp totals -> block -> grid (block_reduce's own first stage sees one meaningful lane per warp)
-  Comp acc[kSums];
-  if ((tid & 31) == 0 && tid < kSweepConsumers) {
-#pragma unroll
-    for (int k = 0; k < kSums; ++k) {
-      const double2 t = s_wacc[tid >> 5][k];
-      acc[k] = Comp(t.x, t.y);
-    }
-  }
-  if (kMoments) {
+  // warp totals -> CTA -> grid. One warp per sum: warp k folds the per-warp totals of sum k (one lane per consumer warp,
+  // fixed shuffle tree), leaves the CTA's total in global memory, and in the last CTA to arrive folds the totals of
+  // all CTAs the same way (lanes stride the blocks). The generic grid_reduce (reduce.cuh) runs every sum through every
+  // warp's shuffle tree twice -- 2-3 us of FP64 work per CTA and date, which a 12.5e6-path shard pays 49 times.
+  __syncthreads();
+  __shared__ bool s_is_last;
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int kCw = kSweepConsumers / 32;
+  static_assert(kCw <= 32, "one lane per consumer warp");
+  for (int ks = warp; ks < kSums; ks += kCw) {
     // back from the doubled cx-space to the reference's x = S - E and y: exact powers of two, and odd powers of x carry
     // the sign of cp
     const double sgn = (double)cp;
-    const double f[8] = {1.0, 0.5 * sgn, 0.25, 0.125 * sgn, 0.0625, 0.5, 0.25 * sgn, 0.125};
-#pragma unroll
-    for (int k = 1; k < kSums; ++k) {
-      acc[k].hi *= f[k];
-      acc[k].lo *= f[k];
+    const double f8[8] = {1.0, 0.5 * sgn, 0.25, 0.125 * sgn, 0.0625, 0.5, 0.25 * sgn, 0.125};
+    const double f = kMoments ? f8[ks] : 1.0;
+    Comp v;
+    if (lane < kCw) {
+      const double2 t = s_wacc[lane][ks];
+      v = Comp(t.x * f, t.y * f);
+    }
+    v = warp_reduce(v);
+    if (lane == 0) {
+      a.partials[((size_t)blockIdx.x * kSums + ks) * 2 + 0] = v.hi;
+      a.partials[((size_t)blockIdx.x * kSums + ks) * 2 + 1] = v.lo;
+      __threadfence();
     }
   }
   __syncthreads();
-  grid_reduce<kSums>(acc, smem, a.partials, a.ticket, a.out, &link);
+  if (tid == 0) s_is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  for (int ks = warp; ks < kSums; ks += kCw) {
+    constexpr int kBatch = 5;  // 5 x 32 >= 148 CTAs: one batch of independent L2 loads, then the dependent adds
+    Comp acc;
+    for (unsigned int b0 = lane; b0 < gridDim.x; b0 += 32 * kBatch) {
+      double2 v[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const unsigned int b = b0 + 32 * j;
+        v[j] = (b < gridDim.x) ? __ldcg(reinterpret_cast<const double2*>(a.partials + ((size_t)b * kSums + ks) * 2))
+                               : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) acc.merge(Comp(v[j].x, v[j].y));
+    }
+    acc = warp_reduce(acc);
+    if (lane == 0) {
+      const double r = acc.value();
+      a.out[ks] = r;
+      smem[ks] = r;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) *a.ticket = 0u;
+  if (link.world > 1) {  // reduce.cuh grid_reduce: the reduction and the collective are one kernel
+    peer_publish<kSums>(link, smem);
+    if (link.gather) {
+      __syncthreads();
+      peer_gather<kSums>(link, smem + 16);
+      if (tid < kSums) a.out[tid] = smem[16 + tid];
+    }
+  }
 }
 
 #ifdef PCF_TUNING
